@@ -1,0 +1,421 @@
+// bf16 x bf16 -> fp32 GEMM on the 5th-gen tensor cores (tcgen05.mma, accumulators in TMEM),
+// operands staged in shared memory by TMA with 128-byte swizzle, fused epilogues.
+//
+// Replaces, on the hot path, every nn.Linear the reference reaches through
+// transformers/models/vit/modeling_vit.py (q/k/v :216-230, attention out :262-268,
+// intermediate :290-299, output :305-312, patch projection :151-167) and their autograd
+// backward GEMMs (cuBLASLt in the reference's stack).
+//
+// One persistent CTA per SM, 10 warps:
+//   warps 0-7  epilogue   (TMEM -> registers -> fused math -> global), 2 warps per TMEM lane quadrant
+//   warp  8    TMA producer (one elected lane)
+//   warp  9    MMA issuer  (one elected lane) + TMEM allocator
+// Three mbarrier pipelines: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue);
+// two 256-column accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// Operand majors (template): K-major = reduction dimension contiguous in memory,
+// MN-major = the M (or N) dimension contiguous. The three GEMMs of a Linear layer map to
+//   forward  Y = X W^T   : A = X  (K-major)   B = W  (K-major)
+//   dgrad    dX = dY W   : A = dY (K-major)   B = W  (MN-major; no transposed weight copy needed)
+//   wgrad    dW = dY^T X : A = dY (MN-major)  B = X  (MN-major), split over the token dimension
+#include "tic_common.cuh"
+
+namespace tic {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BN = 256;
+constexpr int BK = 64;
+constexpr int UMMA_K = 16;
+constexpr int STAGES = 4;
+constexpr int ACC_STAGES = 2;
+constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
+constexpr int B_STAGE_BYTES = BN * BK * 2;  // 32 KB
+constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_THREADS = (NUM_EPI_WARPS + 2) * 32;
+constexpr int TMEM_COLS = ACC_STAGES * BN;  // 512
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+
+enum Epilogue : int {
+  kEpiBf16 = 0,          // out bf16 = acc (+bias)
+  kEpiBf16Gelu = 1,      // out2 bf16 = pre = bf16(acc + bias); out bf16 = gelu(pre)
+  kEpiF32Resid = 2,      // out f32 = acc + bias + aux_f32[m,n]
+  kEpiBf16DGelu = 3,     // out bf16 = bf16(acc) * gelu'(aux_bf16[m,n])
+  kEpiF32 = 4,           // out f32 = acc (+bias)
+  kEpiF32Atomic = 5,     // out f32 += acc (split-K partial, red.global.add)
+  kEpiF32PosEmbed = 6,   // patch embedding: out f32[(m / P) * (P + 1) + 1 + m % P, n] = acc + bias + pos[1 + m % P, n]
+};
+
+struct GemmParams {
+  int M, N, K;
+  int splits;
+  void* out;
+  long long ldo;
+  void* out2;
+  long long ldo2;
+  const float* bias;
+  const void* aux;
+  long long ldaux;
+  int aux_int;  // kEpiF32PosEmbed: patches per image (P)
+};
+
+template <bool A_MN, bool B_MN, int EPI>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                         const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B atoms are 1024 B: align the operand ring.
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* full_bar = bars;                      // [STAGES]   TMA -> MMA
+  uint64_t* empty_bar = bars + STAGES;            // [STAGES]   MMA -> TMA
+  uint64_t* tmem_full_bar = bars + 2 * STAGES;    // [ACC_STAGES] MMA -> epilogue
+  uint64_t* tmem_empty_bar = tmem_full_bar + ACC_STAGES;  // [ACC_STAGES] epilogue -> MMA
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + ACC_STAGES);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int m_blocks = (p.M + BM - 1) / BM;
+  const int n_blocks = (p.N + BN - 1) / BN;
+  const int k_blocks_total = (p.K + BK - 1) / BK;
+  const int k_blocks_per_split = (k_blocks_total + p.splits - 1) / p.splits;
+  const int tiles_per_split = m_blocks * n_blocks;
+  const int total_tiles = tiles_per_split * p.splits;
+
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 9) {
+    if (lane == 0) {
+      for (int i = 0; i < STAGES; ++i) {
+        mbar_init(&full_bar[i], 1);
+        mbar_init(&empty_bar[i], 1);
+      }
+      for (int i = 0; i < ACC_STAGES; ++i) {
+        mbar_init(&tmem_full_bar[i], 1);
+        mbar_init(&tmem_empty_bar[i], NUM_EPI_WARPS);
+      }
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_base_slot, TMEM_COLS);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == 8) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int split = tile / tiles_per_split;
+        const int rem = tile - split * tiles_per_split;
+        const int m_idx = (rem / n_blocks) * BM;
+        const int n_idx = (rem % n_blocks) * BN;
+        const int kb_begin = split * k_blocks_per_split;
+        const int kb_end = min(k_blocks_total, kb_begin + k_blocks_per_split);
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+          uint8_t* sa = smem_a + stage * A_STAGE_BYTES;
+          uint8_t* sb = smem_b + stage * B_STAGE_BYTES;
+          const int k_idx = kb * BK;
+          if constexpr (!A_MN) {
+            tma_load_2d(sa, &tmap_a, &full_bar[stage], k_idx, m_idx);  // box {64 k, 128 rows}
+          } else {
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j)  // boxes {64 m, 64 k}
+              tma_load_2d(sa + j * (64 * BK * 2), &tmap_a, &full_bar[stage], m_idx + 64 * j, k_idx);
+          }
+          if constexpr (!B_MN) {
+            tma_load_2d(sb, &tmap_b, &full_bar[stage], k_idx, n_idx);  // box {64 k, 256 rows}
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)  // boxes {64 n, 64 k}
+              tma_load_2d(sb + j * (64 * BK * 2), &tmap_b, &full_bar[stage], n_idx + 64 * j, k_idx);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 9) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN, B_MN);
+      // K-major SW128: 8-row atoms 1024 B apart (SBO); LBO unused.
+      // MN-major SW128: atoms of 64 (MN) x 8 (K); next 8 k-rows at SBO = 1024 B, next 64-wide MN chunk at
+      // LBO = 64 * BK * 2 = 8192 B (one TMA box).
+      constexpr uint32_t a_lbo = A_MN ? 64 * BK * 2 : 0, b_lbo = B_MN ? 64 * BK * 2 : 0;
+      constexpr uint32_t a_kstep = A_MN ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4;  // desc.lo units of 16 B
+      constexpr uint32_t b_kstep = B_MN ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4;
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc_stage = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int split = tile / tiles_per_split;
+        const int kb_begin = split * k_blocks_per_split;
+        const int kb_end = min(k_blocks_total, kb_begin + k_blocks_per_split);
+        mbar_wait(&tmem_empty_bar[acc_stage], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc_stage * BN;
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t a_desc = make_smem_desc_sw128(smem_u32(smem_a + stage * A_STAGE_BYTES), a_lbo, 1024);
+          const uint64_t b_desc = make_smem_desc_sw128(smem_u32(smem_b + stage * B_STAGE_BYTES), b_lbo, 1024);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            umma_bf16_ss(tmem_d, a_desc + k * a_kstep, b_desc + k * b_kstep, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full_bar[acc_stage]);  // accumulator complete -> epilogue
+        if (++acc_stage == ACC_STAGES) { acc_stage = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps
+    const int quad = warp & 3;   // TMEM lane quadrant this warp may access
+    const int half = warp >> 2;  // which 128-column half of the accumulator
+    int acc_stage = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int split = tile / tiles_per_split;
+      const int rem = tile - split * tiles_per_split;
+      const int m_idx = (rem / n_blocks) * BM;
+      const int n_idx = (rem % n_blocks) * BN;
+      const bool has_k = split * k_blocks_per_split < k_blocks_total;
+      mbar_wait(&tmem_full_bar[acc_stage], acc_phase);
+      tc_fence_after();
+      const int row = m_idx + quad * 32 + lane;
+      const bool row_ok = row < p.M;
+#pragma unroll 1
+      for (int c = 0; c < BN / 2 / 32; ++c) {
+        const int col0 = n_idx + half * (BN / 2) + c * 32;
+        uint32_t r[32];
+        const uint32_t taddr = tmem_base + acc_stage * BN + half * (BN / 2) + c * 32 + (static_cast<uint32_t>(quad * 32) << 16);
+        tmem_ld_32x32b_x32(taddr, r);
+        tmem_ld_wait();
+        if (!row_ok || col0 >= p.N || !has_k) continue;
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+        if constexpr (EPI != kEpiF32Atomic && EPI != kEpiBf16DGelu) {
+          if (p.bias != nullptr) {
+            const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 b = __ldg(b4 + i);
+              v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+            }
+          }
+        }
+        // Columns are handled in groups of 8; N % 8 == 0 is enforced on the host.
+        const int ngroups = min(4, (p.N - col0) >> 3);
+        if constexpr (EPI == kEpiBf16) {
+          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<long long>(row) * p.ldo + col0;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            if (g < ngroups) {
+              uint4 w;
+              w.x = pack_bf16x2(v[8 * g + 0], v[8 * g + 1]); w.y = pack_bf16x2(v[8 * g + 2], v[8 * g + 3]);
+              w.z = pack_bf16x2(v[8 * g + 4], v[8 * g + 5]); w.w = pack_bf16x2(v[8 * g + 6], v[8 * g + 7]);
+              *reinterpret_cast<uint4*>(o + 8 * g) = w;
+            }
+          }
+        } else if constexpr (EPI == kEpiBf16Gelu) {
+          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<long long>(row) * p.ldo + col0;
+          __nv_bfloat16* o2 = reinterpret_cast<__nv_bfloat16*>(p.out2) + static_cast<long long>(row) * p.ldo2 + col0;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            if (g < ngroups) {
+              uint4 w, a;
+              uint32_t* wp = &w.x;
+              uint32_t* ap = &a.x;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                // The reference evaluates GELU on the bf16-rounded fc1 output (autocast).
+                const uint32_t pre = pack_bf16x2(v[8 * g + 2 * j], v[8 * g + 2 * j + 1]);
+                wp[j] = pre;
+                ap[j] = pack_bf16x2(gelu_erf(bf16_lo(pre)), gelu_erf(bf16_hi(pre)));
+              }
+              if (p.out2 != nullptr) *reinterpret_cast<uint4*>(o2 + 8 * g) = w;
+              *reinterpret_cast<uint4*>(o + 8 * g) = a;
+            }
+          }
+        } else if constexpr (EPI == kEpiBf16DGelu) {
+          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<long long>(row) * p.ldo + col0;
+          const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(p.aux) + static_cast<long long>(row) * p.ldaux + col0;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            if (g < ngroups) {
+              const uint4 pre = __ldg(reinterpret_cast<const uint4*>(x + 8 * g));
+              const uint32_t* pp = &pre.x;
+              uint4 w;
+              uint32_t* wp = &w.x;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float g0 = round_bf16(v[8 * g + 2 * j]), g1 = round_bf16(v[8 * g + 2 * j + 1]);
+                wp[j] = pack_bf16x2(g0 * gelu_erf_grad(bf16_lo(pp[j])), g1 * gelu_erf_grad(bf16_hi(pp[j])));
+              }
+              *reinterpret_cast<uint4*>(o + 8 * g) = w;
+            }
+          }
+        } else if constexpr (EPI == kEpiF32Resid) {
+          float* o = reinterpret_cast<float*>(p.out) + static_cast<long long>(row) * p.ldo + col0;
+          const float* x = reinterpret_cast<const float*>(p.aux) + static_cast<long long>(row) * p.ldaux + col0;
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            if (g < 2 * ngroups) {
+              // bf16 GEMM output added to the fp32 residual stream (Appendix B).
+              const float4 a = *reinterpret_cast<const float4*>(x + 4 * g);
+              float4 w;
+              w.x = round_bf16(v[4 * g + 0]) + a.x; w.y = round_bf16(v[4 * g + 1]) + a.y;
+              w.z = round_bf16(v[4 * g + 2]) + a.z; w.w = round_bf16(v[4 * g + 3]) + a.w;
+              *reinterpret_cast<float4*>(o + 4 * g) = w;
+            }
+          }
+        } else if constexpr (EPI == kEpiF32) {
+          float* o = reinterpret_cast<float*>(p.out) + static_cast<long long>(row) * p.ldo + col0;
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            if (g < 2 * ngroups)
+              *reinterpret_cast<float4*>(o + 4 * g) = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+          }
+        } else if constexpr (EPI == kEpiF32Atomic) {
+          float* o = reinterpret_cast<float*>(p.out) + static_cast<long long>(row) * p.ldo + col0;
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            if (g < 2 * ngroups) {
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + 4 * g), "f"(v[4 * g]),
+                           "f"(v[4 * g + 1]), "f"(v[4 * g + 2]), "f"(v[4 * g + 3])
+                           : "memory");
+            }
+          }
+        } else if constexpr (EPI == kEpiF32PosEmbed) {
+          const int P = p.aux_int;
+          const int img = row / P, pidx = row - img * P;
+          float* o = reinterpret_cast<float*>(p.out) + (static_cast<long long>(img) * (P + 1) + 1 + pidx) * p.ldo + col0;
+          const float* x = reinterpret_cast<const float*>(p.aux) + static_cast<long long>(1 + pidx) * p.ldaux + col0;
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            if (g < 2 * ngroups) {
+              const float4 a = __ldg(reinterpret_cast<const float4*>(x + 4 * g));
+              float4 w;
+              w.x = round_bf16(v[4 * g + 0]) + a.x; w.y = round_bf16(v[4 * g + 1]) + a.y;
+              w.z = round_bf16(v[4 * g + 2]) + a.z; w.w = round_bf16(v[4 * g + 3]) + a.w;
+              *reinterpret_cast<float4*>(o + 4 * g) = w;
+            }
+          }
+        }
+      }
+      // All TMEM reads of this warp have completed (wait::ld above): hand the accumulator stage back.
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc_stage]);
+      if (++acc_stage == ACC_STAGES) { acc_stage = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 9) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+int g_num_sms = 0;
+
+int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+template <bool A_MN, bool B_MN, int EPI>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
+  auto kern = gemm_bf16_tcgen05_kernel<A_MN, B_MN, EPI>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) return set_error(kErrCuda, "gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int m_blocks = (p.M + BM - 1) / BM, n_blocks = (p.N + BN - 1) / BN;
+  const int total = m_blocks * n_blocks * p.splits;
+  const int grid = total < num_sms() ? total : num_sms();
+  kern<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, p);
+  return check_launch("gemm_bf16_tcgen05");
+}
+
+}  // namespace
+
+// A: K-major => [M, K] row-major with pitch lda; MN-major => [K, M] row-major with pitch lda.
+// B: K-major => [N, K] row-major with pitch ldb; MN-major => [K, N] row-major with pitch ldb.
+int gemm_bf16(const void* A, long long lda, bool a_mn, const void* B, long long ldb, bool b_mn, int M, int N, int K,
+              int epilogue, void* out, long long ldo, void* out2, long long ldo2, const float* bias, const void* aux,
+              long long ldaux, int aux_int, int splits, cudaStream_t stream) {
+  if (M <= 0 || N <= 0 || K <= 0) return set_error(kErrInvalidArg, "gemm: empty problem %dx%dx%d", M, N, K);
+  if (N % 8 != 0) return set_error(kErrInvalidArg, "gemm: N=%d must be a multiple of 8", N);
+  if ((lda % 8) || (ldb % 8)) return set_error(kErrInvalidArg, "gemm: operand pitches must be multiples of 8 elements");
+  if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15) ||
+      (reinterpret_cast<uintptr_t>(out) & 15))
+    return set_error(kErrInvalidArg, "gemm: pointers must be 16-byte aligned");
+  const int k_blocks = (K + BK - 1) / BK;
+  if (splits < 1) splits = 1;
+  if (splits > k_blocks) splits = k_blocks;
+  {  // make every split non-empty
+    const int per = (k_blocks + splits - 1) / splits;
+    splits = (k_blocks + per - 1) / per;
+  }
+  if (splits > 1 && epilogue != kEpiF32Atomic)
+    return set_error(kErrInvalidArg, "gemm: split-K requires the atomic fp32 epilogue");
+
+  CUtensorMap ta, tb;
+  int rc;
+  if (!a_mn) rc = encode_tmap_2d_bf16(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, 64, BM);
+  else       rc = encode_tmap_2d_bf16(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 64, BK);
+  if (rc) return rc;
+  if (!b_mn) rc = encode_tmap_2d_bf16(&tb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, 64, BN);
+  else       rc = encode_tmap_2d_bf16(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, BK);
+  if (rc) return rc;
+
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K; p.splits = splits;
+  p.out = out; p.ldo = ldo; p.out2 = out2; p.ldo2 = ldo2;
+  p.bias = bias; p.aux = aux; p.ldaux = ldaux; p.aux_int = aux_int;
+
+#define TIC_GEMM_CASE(AMN, BMN, E) \
+  if (a_mn == AMN && b_mn == BMN && epilogue == E) return launch<AMN, BMN, E>(ta, tb, p, stream);
+  // forward (K-major x K-major)
+  TIC_GEMM_CASE(false, false, kEpiBf16)
+  TIC_GEMM_CASE(false, false, kEpiBf16Gelu)
+  TIC_GEMM_CASE(false, false, kEpiF32Resid)
+  TIC_GEMM_CASE(false, false, kEpiF32)
+  TIC_GEMM_CASE(false, false, kEpiF32PosEmbed)
+  // dgrad (K-major x MN-major)
+  TIC_GEMM_CASE(false, true, kEpiBf16)
+  TIC_GEMM_CASE(false, true, kEpiBf16DGelu)
+  TIC_GEMM_CASE(false, true, kEpiF32)
+  // wgrad (MN-major x MN-major)
+  TIC_GEMM_CASE(true, true, kEpiF32)
+  TIC_GEMM_CASE(true, true, kEpiF32Atomic)
+#undef TIC_GEMM_CASE
+  return set_error(kErrUnsupported, "gemm: no kernel for a_mn=%d b_mn=%d epilogue=%d", (int)a_mn, (int)b_mn, epilogue);
+}
+
+}  // namespace tic
