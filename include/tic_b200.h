@@ -64,6 +64,98 @@ TIC_API int tic_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void
                           int M, int N, int K, int epilogue, void* out, int64_t ldo, void* out2, int64_t ldo2,
                           const float* bias, const void* aux, int64_t ldaux, int aux_int, int splits, void* stream);
 
+
+/* ---- LayerNorm ---------------------------------------------------------------------------------
+ * Replaces nn.LayerNorm (modeling_vit.py:325-326,333,340,455) [a4, a11]. fp32 statistics, eps from
+ * ViTConfig.layer_norm_eps. Row pitches are in elements; y_bf16 / y_f32 / mean / rstd may be NULL.
+ * Backward: dx = dres + LN'(dy) (dres may alias dx or be NULL); dgamma / dbeta are ACCUMULATED. */
+TIC_API int tic_layernorm_fwd(const float* x, int64_t ldx, const float* gamma, const float* beta, float eps, int rows,
+                              int D, void* y_bf16, int64_t ldy, float* y_f32, int64_t ldyf, float* mean, float* rstd,
+                              void* stream);
+TIC_API int tic_layernorm_bwd(const void* dy_bf16, int64_t lddy, const float* x, int64_t ldx, const float* mean,
+                              const float* rstd, const float* gamma, const float* dres, int64_t lddres, int rows, int D,
+                              float* dx, int64_t lddx, void* dx_bf16, int64_t lddxb, float* dgamma, float* dbeta,
+                              void* stream);
+
+/* ---- fused multi-head attention -----------------------------------------------------------------
+ * Replaces F.scaled_dot_product_attention (modeling_vit.py:232-246; sdpa_attention.py:92-103) [a6].
+ * q/k/v are token-major [B*N, ...] with row pitch ld (elements) and head h at column h*64; o is
+ * [B*N, H*64] with pitch ldo. lse is [B, H, N] fp32 (NULL to skip). head_dim must be 64. */
+TIC_API int tic_attention_fwd(const void* q, const void* k, const void* v, int64_t ld, void* o, int64_t ldo, float* lse,
+                              int B, int N, int H, int head_dim, float scale, void* stream);
+TIC_API int tic_attention_bwd(const void* q, const void* k, const void* v, int64_t ld, const void* o, int64_t ldo,
+                              const void* dout, int64_t lddo, const float* lse, float* delta_scratch, void* dq, void* dk,
+                              void* dv, int64_t lddqkv, int B, int N, int H, int head_dim, float scale, void* stream);
+
+/* ---- classifier head and fused softmax cross-entropy ----------------------------------------------
+ * tic_head_fwd: logits[B,C] = h[B,D] W[C,D]^T + b (classifier, modeling_vit.py:641-642 [a11]).
+ * tic_softmax_xent: F.cross_entropy forward + backward in one launch, integer targets (finetune.py:61
+ * [a13]) or soft targets from MixUp/CutMix (ntrain.py:48 [a15]); exactly one of hard/soft non-NULL.
+ * loss = mean over the B rows; dlogits = (softmax * sum(y) - y) * grad_scale; correct = #argmax==hard. */
+TIC_API int tic_head_fwd(const void* h_bf16, int64_t ldh, const void* w_bf16, const float* bias, int B, int D, int C,
+                         int round_out_bf16, float* logits, void* stream);
+TIC_API int tic_head_bwd(const float* dlogits, const void* h_bf16, int64_t ldh, const void* w_bf16, int B, int D, int C,
+                         void* dh_bf16, int64_t lddh, float* dW_accum, float* db_accum, void* stream);
+TIC_API int tic_softmax_xent(const float* logits, const int64_t* hard, const float* soft, int B, int C,
+                             float grad_scale, int round_grad_bf16, float* loss, float* dlogits, int32_t* correct,
+                             void* stream);
+
+/* ---- fused AdamW --------------------------------------------------------------------------------
+ * Replaces torch.optim.AdamW.step as configured at ntrain.py:39-41 [a16] / finetune.py:314 over a flat
+ * fp32 arena (n % 4 == 0); also writes the bf16 shadow (may be NULL). `step` is 1-based. Gradients are
+ * multiplied by grad_scale first (1/world_size after a sum-allreduce, or 1). */
+TIC_API int tic_adamw_step(float* p, const float* g, float* m, float* v, void* shadow_bf16, int64_t n, float lr,
+                           float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
+                           void* stream);
+
+/* ---- elementwise glue ---------------------------------------------------------------------------- */
+/* fp32 NCHW [B,3,S,S] -> bf16 patch rows [B*(S/16)^2, 768], K ordered (c, py, px) (modeling_vit.py:151,166 [a2]) */
+TIC_API int tic_patchify_f32(const float* pixels, void* patches_bf16, int B, int S, void* stream);
+TIC_API int tic_cast_f32_to_bf16(const float* src, void* dst_bf16, int64_t n, void* stream);
+TIC_API int tic_cast_bf16_to_f32(const void* src_bf16, float* dst, int64_t n, void* stream);
+/* out[n] += sum_m dy[m, n] (bias gradients) */
+TIC_API int tic_colsum_bf16(const void* dy_bf16, int64_t ld, int rows, int cols, float* out_accum, void* stream);
+
+/* ---- whole-model engine ---------------------------------------------------------------------------
+ * Stands where ViTForImageClassification.forward (modeling_vit.py:620-653) and its autograd backward
+ * stand in the reference [a2-a12]. Parameters live in one fp32 arena whose element offsets are reported
+ * by tic_vit_param_layout in HF named_parameters() order:
+ *   cls_token, position_embeddings, patch.weight, patch.bias,
+ *   per layer: q.w q.b k.w k.b v.w v.b attn_out.w attn_out.b fc1.w fc1.b fc2.w fc2.b ln_before.w ln_before.b
+ *              ln_after.w ln_after.b,
+ *   layernorm.w, layernorm.b, classifier.w, classifier.b               => 4 + 16*layers + 4 tensors.
+ * The bf16 shadow and the gradient arena use the same offsets. */
+typedef struct tic_vit_config {
+  int32_t image_size;  /* 224 or 384 */
+  int32_t patch_size;  /* 16 */
+  int32_t hidden;      /* 768 / 1024 */
+  int32_t layers;      /* 12 / 24 */
+  int32_t heads;       /* 12 / 16 (head_dim 64) */
+  int32_t mlp;         /* 3072 / 4096 */
+  int32_t num_labels;  /* 120 */
+  float ln_eps;        /* 1e-12 */
+} tic_vit_config;
+
+TIC_API int64_t tic_vit_param_arena_elems(const tic_vit_config* cfg);
+/* Fills offsets[i], numels[i] for tensor i in HF order; returns the number of tensors, or -1 on error. */
+TIC_API int tic_vit_param_layout(const tic_vit_config* cfg, int64_t* offsets, int64_t* numels, int max_tensors);
+/* Element offset where the classifier (the only part trained when full_finetune=False, ntrain.py:35-37) begins. */
+TIC_API int64_t tic_vit_head_offset(const tic_vit_config* cfg);
+/* Element range [begin, end) of the gradient arena that backward stage `stage` completes (for bucketed allreduce). */
+TIC_API int tic_vit_stage_grad_range(const tic_vit_config* cfg, int stage, int64_t* begin, int64_t* end);
+TIC_API int64_t tic_vit_workspace_bytes(const tic_vit_config* cfg, int batch, int training);
+/* Exactly one of pixels (fp32 [B,3,S,S]) / patches_bf16 ([B*P,768], e.g. from tic_augment_patchify) is non-NULL.
+ * training != 0 keeps the activations the backward needs in `workspace`. logits: fp32 [B, num_labels]. */
+TIC_API int tic_vit_forward(const tic_vit_config* cfg, const float* params_f32, const void* params_bf16,
+                            const float* pixels, const void* patches_bf16, int batch, void* workspace,
+                            int64_t workspace_bytes, int training, float* logits, void* stream);
+/* Backward stages: 0 = classifier + final LayerNorm, 1..layers = encoder layers (last first), layers+1 = embeddings.
+ * Runs stages [stage_begin, stage_end) and ACCUMULATES parameter gradients into grads_f32 (arena layout).
+ * head_only != 0 computes only the classifier gradients (frozen backbone). */
+TIC_API int tic_vit_backward(const tic_vit_config* cfg, const float* params_f32, const void* params_bf16, int batch,
+                             void* workspace, int64_t workspace_bytes, const float* dlogits, float* grads_f32,
+                             int stage_begin, int stage_end, int head_only, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

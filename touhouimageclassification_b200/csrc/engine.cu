@@ -1,0 +1,331 @@
+// Native ViT engine: one C call runs the whole encoder forward (or backward) as a fixed sequence of
+// kernel launches on the caller's stream -- no Python between kernels, no allocation, graph-capturable.
+// Mirrors ViTForImageClassification.forward (modeling_vit.py:620-653) = ViTEmbeddings (:100-128) +
+// Lyr x ViTLayer (:328-346) + final LayerNorm (:455) + classifier on the CLS row (:641-642) [a2-a12],
+// and the autograd backward of the same graph.
+//
+// Memory model (all caller-provided):
+//   parameter arena  fp32, private order (see vit_layout) with q/k/v contiguous so the QKV projection is
+//                    one [3D, D] GEMM; the nn.Parameters on the Python side are views into it.
+//   bf16 shadow      same layout, GEMM operands; refreshed by the fused AdamW or tic_cast_f32_to_bf16.
+//   gradient arena   fp32, same layout; backward ACCUMULATES into it (caller zeroes it per step).
+//   workspace        activations saved for backward + scratch, carved by vit_workspace().
+#include "tic_b200.h"
+#include "tic_internal.cuh"
+
+namespace tic {
+
+namespace {
+inline long long align_up(long long v, long long a) { return (v + a - 1) / a * a; }
+}  // namespace
+
+int vit_validate(const tic_vit_config* c) {
+  if (c == nullptr) return set_error(kErrInvalidArg, "vit: null config");
+  if (c->patch_size != 16) return set_error(kErrUnsupported, "vit: patch_size=%d (only 16)", c->patch_size);
+  if (c->image_size <= 0 || c->image_size % 16) return set_error(kErrInvalidArg, "vit: bad image_size=%d", c->image_size);
+  if (c->hidden % 128 || c->hidden <= 0) return set_error(kErrUnsupported, "vit: hidden=%d must be a multiple of 128", c->hidden);
+  if (c->heads <= 0 || c->hidden != c->heads * 64) return set_error(kErrUnsupported, "vit: head_dim must be 64 (hidden=%d heads=%d)", c->hidden, c->heads);
+  if (c->mlp % 8 || c->mlp <= 0) return set_error(kErrInvalidArg, "vit: bad mlp=%d", c->mlp);
+  if (c->layers <= 0 || c->num_labels <= 0) return set_error(kErrInvalidArg, "vit: bad layers/num_labels");
+  return kOk;
+}
+
+VitLayout vit_layout(const tic_vit_config* c) {
+  VitLayout L;
+  const long long D = c->hidden, F = c->mlp, C = c->num_labels;
+  const long long G = c->image_size / 16, N = G * G + 1;
+  long long off = 0;
+  auto take = [&](long long n) { long long o = off; off += align_up(n, 64); return o; };
+  L.cls = take(D);
+  L.pos = take(N * D);
+  L.patch_w = take(D * 768);
+  L.patch_b = take(D);
+  L.layer0 = off;
+  long long lo = 0;
+  auto ltake = [&](long long n) { long long o = lo; lo += align_up(n, 64); return o; };
+  L.qkv_w = ltake(3 * D * D);
+  L.qkv_b = ltake(3 * D);
+  L.o_w = ltake(D * D);
+  L.o_b = ltake(D);
+  L.fc1_w = ltake(F * D);
+  L.fc1_b = ltake(F);
+  L.fc2_w = ltake(D * F);
+  L.fc2_b = ltake(D);
+  L.ln1_w = ltake(D);
+  L.ln1_b = ltake(D);
+  L.ln2_w = ltake(D);
+  L.ln2_b = ltake(D);
+  L.layer_stride = lo;
+  off += lo * c->layers;
+  L.lnf_w = take(D);
+  L.lnf_b = take(D);
+  L.head_begin = off;
+  L.cls_w = take(C * D);
+  L.cls_b = take(C);
+  L.total = off;
+  return L;
+}
+
+namespace {
+
+struct Workspace {
+  // saved for backward (training) / scratch (inference)
+  long long patches, x, xmid, h1, qkv, ctx, lse, h2, pre, act, stats, hcls, logits_scratch;
+  // backward scratch
+  long long dx, dxb, dact, dh, dqkv, dctx, delta, dhcls, dpatch;
+  long long total;
+  // strides between per-layer copies (0 in inference mode: buffers are reused)
+  long long s_x, s_tok_d_bf16, s_qkv, s_lse, s_f, s_stats;
+};
+
+Workspace carve(const tic_vit_config* c, int B, bool training) {
+  Workspace w{};
+  const long long D = c->hidden, F = c->mlp, H = c->heads, Lyr = c->layers;
+  const long long G = c->image_size / 16, N = G * G + 1, P = N - 1, M = static_cast<long long>(B) * N;
+  long long off = 0;
+  auto take = [&](long long bytes) { long long o = off; off += align_up(bytes, 1024); return o; };
+  const long long nl = training ? Lyr : 1;
+  w.patches = take(static_cast<long long>(B) * P * 768 * 2);
+  w.s_x = align_up(M * D * 4, 1024);
+  w.x = take(w.s_x * (training ? Lyr + 1 : 1));
+  w.xmid = take(w.s_x * nl);
+  w.s_tok_d_bf16 = align_up(M * D * 2, 1024);
+  w.h1 = take(w.s_tok_d_bf16 * nl);
+  w.s_qkv = align_up(M * 3 * D * 2, 1024);
+  w.qkv = take(w.s_qkv * nl);
+  w.ctx = take(w.s_tok_d_bf16 * nl);
+  w.s_lse = align_up(static_cast<long long>(B) * H * N * 4, 1024);
+  w.lse = take(w.s_lse * nl);
+  w.h2 = take(w.s_tok_d_bf16 * nl);
+  w.s_f = align_up(M * F * 2, 1024);
+  w.pre = training ? take(w.s_f * nl) : 0;
+  w.act = take(w.s_f * nl);
+  w.s_stats = align_up(M * 4, 1024);
+  w.stats = take(w.s_stats * 4 * nl + static_cast<long long>(B) * 8 + 1024);  // ln1/ln2 mean+rstd per layer, then final LN
+  w.hcls = take(static_cast<long long>(B) * D * 2);
+  w.logits_scratch = take(static_cast<long long>(B) * c->num_labels * 4);
+  if (training) {
+    w.dx = take(M * D * 4);
+    w.dxb = take(M * D * 2);
+    w.dact = take(M * F * 2);
+    w.dh = take(M * D * 2);
+    w.dqkv = take(M * 3 * D * 2);
+    w.dctx = take(M * D * 2);
+    w.delta = take(static_cast<long long>(B) * H * N * 4);
+    w.dhcls = take(static_cast<long long>(B) * D * 2);
+    w.dpatch = take(static_cast<long long>(B) * P * D * 2);
+  } else {
+    w.s_x = w.s_tok_d_bf16 = w.s_qkv = w.s_lse = w.s_f = w.s_stats = 0;
+  }
+  w.total = off;
+  return w;
+}
+
+// Pick a split-K factor for a wgrad GEMM so that tiles * splits fills whole waves of 148 CTAs.
+int pick_splits(int Mo, int No, int K) {
+  const int tiles = ((Mo + 127) / 128) * ((No + 255) / 256);
+  const int kblocks = (K + 63) / 64;
+  int best = 1;
+  double best_eff = 0.0;
+  for (int s = 1; s <= 64; ++s) {
+    if (s > 1 && kblocks / s < 16) break;
+    const long long t = static_cast<long long>(tiles) * s;
+    const double eff = static_cast<double>(t) / (static_cast<double>((t + 147) / 148) * 148.0);
+    if (eff > best_eff + 0.02) { best_eff = eff; best = s; }
+  }
+  return best;
+}
+
+#define TIC_TRY(expr)        \
+  do {                       \
+    int rc__ = (expr);       \
+    if (rc__ != kOk) return rc__; \
+  } while (0)
+
+}  // namespace
+
+long long vit_workspace_bytes(const tic_vit_config* c, int B, int training) {
+  return carve(c, B, training != 0).total;
+}
+
+int vit_forward(const tic_vit_config* c, const float* P32, const void* P16v, const float* pixels,
+                const void* patches_in, int B, void* workspace, long long workspace_bytes, int training,
+                float* logits, cudaStream_t st) {
+  TIC_TRY(vit_validate(c));
+  if (B <= 0) return set_error(kErrInvalidArg, "vit_forward: empty batch");
+  const Workspace w = carve(c, B, training != 0);
+  if (workspace_bytes < w.total)
+    return set_error(kErrInvalidArg, "vit_forward: workspace too small (%lld < %lld bytes)", workspace_bytes, w.total);
+  if ((pixels == nullptr) == (patches_in == nullptr))
+    return set_error(kErrInvalidArg, "vit_forward: give exactly one of pixels / patches");
+  const VitLayout L = vit_layout(c);
+  const __nv_bfloat16* P16 = reinterpret_cast<const __nv_bfloat16*>(P16v);
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  const int D = c->hidden, F = c->mlp, H = c->heads, C = c->num_labels, S = c->image_size;
+  const int G = S / 16, N = G * G + 1, Pn = N - 1;
+  const int M = B * N;
+  const float scale = 0.125f;  // 1 / sqrt(head_dim = 64)
+
+  // ---- embeddings: patchify -> projection GEMM (+bias, +pos) -> CLS rows
+  const void* patches = patches_in;
+  if (pixels != nullptr) {
+    TIC_TRY(patchify_f32(pixels, ws + w.patches, B, S, st));
+    patches = ws + w.patches;
+  } else if (training) {
+    // keep a copy for the patch-projection wgrad
+    cudaError_t e = cudaMemcpyAsync(ws + w.patches, patches_in, static_cast<size_t>(B) * Pn * 768 * 2,
+                                    cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) return set_error(kErrCuda, "vit_forward: memcpy patches: %s", cudaGetErrorString(e));
+    patches = ws + w.patches;
+  }
+  float* x0 = reinterpret_cast<float*>(ws + w.x);
+  TIC_TRY(gemm_bf16(patches, 768, false, P16 + L.patch_w, 768, false, B * Pn, D, 768, kEpiF32PosEmbed, x0, D, nullptr, 0,
+                    P32 + L.patch_b, P32 + L.pos, D, Pn, 1, st));
+  TIC_TRY(cls_rows(P32 + L.cls, P32 + L.pos, x0, B, N, D, st));
+
+  // ---- encoder
+  for (int l = 0; l < c->layers; ++l) {
+    const long long po = L.layer0 + static_cast<long long>(l) * L.layer_stride;
+    const float* p32 = P32 + po;
+    const __nv_bfloat16* p16 = P16 + po;
+    float* x_in = reinterpret_cast<float*>(ws + w.x + w.s_x * l);
+    float* x_out = reinterpret_cast<float*>(ws + w.x + w.s_x * (training ? l + 1 : 0));
+    float* xmid = reinterpret_cast<float*>(ws + w.xmid + w.s_x * l);
+    void* h1 = ws + w.h1 + w.s_tok_d_bf16 * l;
+    __nv_bfloat16* qkv = reinterpret_cast<__nv_bfloat16*>(ws + w.qkv + w.s_qkv * l);
+    void* ctx = ws + w.ctx + w.s_tok_d_bf16 * l;
+    float* lse = reinterpret_cast<float*>(ws + w.lse + w.s_lse * l);
+    void* h2 = ws + w.h2 + w.s_tok_d_bf16 * l;
+    void* pre = training ? ws + w.pre + w.s_f * l : nullptr;
+    void* act = ws + w.act + w.s_f * l;
+    float* stats = reinterpret_cast<float*>(ws + w.stats + w.s_stats * 4 * l);
+    const long long ss = w.s_stats / 4;
+    float *mean1 = training ? stats : nullptr, *rstd1 = training ? stats + ss : nullptr;
+    float *mean2 = training ? stats + 2 * ss : nullptr, *rstd2 = training ? stats + 3 * ss : nullptr;
+
+    TIC_TRY(layernorm_fwd(x_in, D, p32 + L.ln1_w, p32 + L.ln1_b, c->ln_eps, M, D, h1, D, nullptr, 0, mean1, rstd1, st));
+    TIC_TRY(gemm_bf16(h1, D, false, p16 + L.qkv_w, D, false, M, 3 * D, D, kEpiBf16, qkv, 3 * D, nullptr, 0,
+                      p32 + L.qkv_b, nullptr, 0, 0, 1, st));
+    TIC_TRY(attention_fwd(qkv, qkv + D, qkv + 2 * D, 3 * D, ctx, D, training ? lse : nullptr, B, N, H, 64, scale, st));
+    TIC_TRY(gemm_bf16(ctx, D, false, p16 + L.o_w, D, false, M, D, D, kEpiF32Resid, xmid, D, nullptr, 0, p32 + L.o_b,
+                      x_in, D, 0, 1, st));
+    TIC_TRY(layernorm_fwd(xmid, D, p32 + L.ln2_w, p32 + L.ln2_b, c->ln_eps, M, D, h2, D, nullptr, 0, mean2, rstd2, st));
+    TIC_TRY(gemm_bf16(h2, D, false, p16 + L.fc1_w, D, false, M, F, D, kEpiBf16Gelu, act, F, pre, F, p32 + L.fc1_b,
+                      nullptr, 0, 0, 1, st));
+    TIC_TRY(gemm_bf16(act, F, false, p16 + L.fc2_w, F, false, M, D, F, kEpiF32Resid, x_out, D, nullptr, 0,
+                      p32 + L.fc2_b, xmid, D, 0, 1, st));
+  }
+
+  // ---- final LayerNorm on the CLS rows only (the only rows the classifier reads) + head
+  float* x_last = reinterpret_cast<float*>(ws + w.x + w.s_x * (training ? c->layers : 0));
+  float* fstats = reinterpret_cast<float*>(ws + w.stats + w.s_stats * 4 * (training ? c->layers : 0));
+  TIC_TRY(layernorm_fwd(x_last, static_cast<long long>(N) * D, P32 + L.lnf_w, P32 + L.lnf_b, c->ln_eps, B, D,
+                        ws + w.hcls, D, nullptr, 0, fstats, fstats + B, st));
+  TIC_TRY(head_fwd(ws + w.hcls, D, P16 + L.cls_w, P32 + L.cls_b, B, D, C, 1, logits, st));
+  return kOk;
+}
+
+// stage 0 = classifier + final LayerNorm, stages 1..Lyr = encoder layers Lyr-1..0, stage Lyr+1 = embeddings.
+int vit_backward(const tic_vit_config* c, const float* P32, const void* P16v, int B, void* workspace,
+                 long long workspace_bytes, const float* dlogits, float* G, int stage_begin, int stage_end,
+                 int head_only, cudaStream_t st) {
+  TIC_TRY(vit_validate(c));
+  const Workspace w = carve(c, B, true);
+  if (workspace_bytes < w.total)
+    return set_error(kErrInvalidArg, "vit_backward: workspace too small (%lld < %lld bytes)", workspace_bytes, w.total);
+  const VitLayout L = vit_layout(c);
+  const __nv_bfloat16* P16 = reinterpret_cast<const __nv_bfloat16*>(P16v);
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  const int D = c->hidden, F = c->mlp, H = c->heads, C = c->num_labels, Lyr = c->layers;
+  const int Gd = c->image_size / 16, N = Gd * Gd + 1, Pn = N - 1;
+  const int M = B * N;
+  const float scale = 0.125f;
+  float* dx = reinterpret_cast<float*>(ws + w.dx);
+  __nv_bfloat16* dxb = reinterpret_cast<__nv_bfloat16*>(ws + w.dxb);
+  void* dact = ws + w.dact;
+  void* dh = ws + w.dh;
+  __nv_bfloat16* dqkv = reinterpret_cast<__nv_bfloat16*>(ws + w.dqkv);
+  void* dctx = ws + w.dctx;
+  float* delta = reinterpret_cast<float*>(ws + w.delta);
+  if (stage_begin < 0) stage_begin = 0;
+  if (stage_end > Lyr + 2) stage_end = Lyr + 2;
+
+  for (int stage = stage_begin; stage < stage_end; ++stage) {
+    if (stage == 0) {
+      const bool need_dh = !head_only;
+      TIC_TRY(head_bwd(dlogits, ws + w.hcls, D, P16 + L.cls_w, B, D, C, need_dh ? ws + w.dhcls : nullptr, D,
+                       G + L.cls_w, G + L.cls_b, st));
+      if (head_only) continue;
+      cudaError_t e1 = cudaMemsetAsync(dx, 0, static_cast<size_t>(M) * D * 4, st);
+      cudaError_t e2 = cudaMemsetAsync(dxb, 0, static_cast<size_t>(M) * D * 2, st);
+      if (e1 != cudaSuccess || e2 != cudaSuccess) return set_error(kErrCuda, "vit_backward: memset failed");
+      const float* x_last = reinterpret_cast<const float*>(ws + w.x + w.s_x * Lyr);
+      const float* fstats = reinterpret_cast<const float*>(ws + w.stats + w.s_stats * 4 * Lyr);
+      const long long rs = static_cast<long long>(N) * D;
+      TIC_TRY(layernorm_bwd(ws + w.dhcls, D, x_last, rs, fstats, fstats + B, P32 + L.lnf_w, nullptr, 0, B, D, dx, rs,
+                            dxb, rs, G + L.lnf_w, G + L.lnf_b, st));
+    } else if (stage <= Lyr) {
+      if (head_only) continue;
+      const int l = Lyr - stage;
+      const long long po = L.layer0 + static_cast<long long>(l) * L.layer_stride;
+      const float* p32 = P32 + po;
+      const __nv_bfloat16* p16 = P16 + po;
+      float* g = G + po;
+      const float* x_in = reinterpret_cast<const float*>(ws + w.x + w.s_x * l);
+      const float* xmid = reinterpret_cast<const float*>(ws + w.xmid + w.s_x * l);
+      const void* h1 = ws + w.h1 + w.s_tok_d_bf16 * l;
+      const __nv_bfloat16* qkv = reinterpret_cast<const __nv_bfloat16*>(ws + w.qkv + w.s_qkv * l);
+      const void* ctx = ws + w.ctx + w.s_tok_d_bf16 * l;
+      const float* lse = reinterpret_cast<const float*>(ws + w.lse + w.s_lse * l);
+      const void* h2 = ws + w.h2 + w.s_tok_d_bf16 * l;
+      const void* pre = ws + w.pre + w.s_f * l;
+      const void* act = ws + w.act + w.s_f * l;
+      const float* stats = reinterpret_cast<const float*>(ws + w.stats + w.s_stats * 4 * l);
+      const long long ss = w.s_stats / 4;
+      const float *mean1 = stats, *rstd1 = stats + ss, *mean2 = stats + 2 * ss, *rstd2 = stats + 3 * ss;
+
+      // fc2: x_out = xmid + act W2^T + b2        (dy = dxb, the bf16 copy of the residual-stream gradient)
+      TIC_TRY(gemm_bf16(dxb, D, false, p16 + L.fc2_w, F, true, M, F, D, kEpiBf16DGelu, dact, F, nullptr, 0, nullptr, pre,
+                        F, 0, 1, st));  // dact <- dpre = (dy W2) * gelu'(pre)
+      TIC_TRY(gemm_bf16(dxb, D, true, act, F, true, D, F, M, kEpiF32Atomic, g + L.fc2_w, F, nullptr, 0, nullptr, nullptr,
+                        0, 0, pick_splits(D, F, M), st));
+      TIC_TRY(colsum_bf16(dxb, D, M, D, g + L.fc2_b, st));
+      // fc1: pre = h2 W1^T + b1
+      TIC_TRY(gemm_bf16(dact, F, false, p16 + L.fc1_w, D, true, M, D, F, kEpiBf16, dh, D, nullptr, 0, nullptr, nullptr, 0,
+                        0, 1, st));
+      TIC_TRY(gemm_bf16(dact, F, true, h2, D, true, F, D, M, kEpiF32Atomic, g + L.fc1_w, D, nullptr, 0, nullptr, nullptr,
+                        0, 0, pick_splits(F, D, M), st));
+      TIC_TRY(colsum_bf16(dact, F, M, F, g + L.fc1_b, st));
+      // layernorm_after + residual
+      TIC_TRY(layernorm_bwd(dh, D, xmid, D, mean2, rstd2, p32 + L.ln2_w, dx, D, M, D, dx, D, dxb, D, g + L.ln2_w,
+                            g + L.ln2_b, st));
+      // attention output projection: xmid = x_in + ctx Wo^T + bo
+      TIC_TRY(gemm_bf16(dxb, D, false, p16 + L.o_w, D, true, M, D, D, kEpiBf16, dctx, D, nullptr, 0, nullptr, nullptr, 0,
+                        0, 1, st));
+      TIC_TRY(gemm_bf16(dxb, D, true, ctx, D, true, D, D, M, kEpiF32Atomic, g + L.o_w, D, nullptr, 0, nullptr, nullptr, 0,
+                        0, pick_splits(D, D, M), st));
+      TIC_TRY(colsum_bf16(dxb, D, M, D, g + L.o_b, st));
+      // attention core
+      TIC_TRY(attention_bwd(qkv, qkv + D, qkv + 2 * D, 3 * D, ctx, D, dctx, D, lse, delta, dqkv, dqkv + D, dqkv + 2 * D,
+                            3 * D, B, N, H, 64, scale, st));
+      // fused QKV projection
+      TIC_TRY(gemm_bf16(dqkv, 3 * D, false, p16 + L.qkv_w, D, true, M, D, 3 * D, kEpiBf16, dh, D, nullptr, 0, nullptr,
+                        nullptr, 0, 0, 1, st));
+      TIC_TRY(gemm_bf16(dqkv, 3 * D, true, h1, D, true, 3 * D, D, M, kEpiF32Atomic, g + L.qkv_w, D, nullptr, 0, nullptr,
+                        nullptr, 0, 0, pick_splits(3 * D, D, M), st));
+      TIC_TRY(colsum_bf16(dqkv, 3 * D, M, 3 * D, g + L.qkv_b, st));
+      // layernorm_before + residual
+      TIC_TRY(layernorm_bwd(dh, D, x_in, D, mean1, rstd1, p32 + L.ln1_w, dx, D, M, D, dx, D, l > 0 ? dxb : nullptr, D,
+                            g + L.ln1_w, g + L.ln1_b, st));
+    } else {
+      if (head_only) continue;
+      TIC_TRY(embed_bwd(dx, B, N, D, G + L.pos, G + L.cls, ws + w.dpatch, st));
+      TIC_TRY(gemm_bf16(ws + w.dpatch, D, true, ws + w.patches, 768, true, D, 768, B * Pn, kEpiF32Atomic, G + L.patch_w,
+                        768, nullptr, 0, nullptr, nullptr, 0, 0, pick_splits(D, 768, B * Pn), st));
+      TIC_TRY(colsum_bf16(ws + w.dpatch, D, B * Pn, D, G + L.patch_b, st));
+    }
+  }
+  return kOk;
+}
+
+}  // namespace tic

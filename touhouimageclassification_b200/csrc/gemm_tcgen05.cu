@@ -18,7 +18,7 @@
 //   forward  Y = X W^T   : A = X  (K-major)   B = W  (K-major)
 //   dgrad    dX = dY W   : A = dY (K-major)   B = W  (MN-major; no transposed weight copy needed)
 //   wgrad    dW = dY^T X : A = dY (MN-major)  B = X  (MN-major), split over the token dimension
-#include "tic_common.cuh"
+#include "tic_internal.cuh"
 
 namespace tic {
 
@@ -38,15 +38,6 @@ constexpr int NUM_THREADS = (NUM_EPI_WARPS + 2) * 32;
 constexpr int TMEM_COLS = ACC_STAGES * BN;  // 512
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 
-enum Epilogue : int {
-  kEpiBf16 = 0,          // out bf16 = acc (+bias)
-  kEpiBf16Gelu = 1,      // out2 bf16 = pre = bf16(acc + bias); out bf16 = gelu(pre)
-  kEpiF32Resid = 2,      // out f32 = acc + bias + aux_f32[m,n]
-  kEpiBf16DGelu = 3,     // out bf16 = bf16(acc) * gelu'(aux_bf16[m,n])
-  kEpiF32 = 4,           // out f32 = acc (+bias)
-  kEpiF32Atomic = 5,     // out f32 += acc (split-K partial, red.global.add)
-  kEpiF32PosEmbed = 6,   // patch embedding: out f32[(m / P) * (P + 1) + 1 + m % P, n] = acc + bias + pos[1 + m % P, n]
-};
 
 struct GemmParams {
   int M, N, K;

@@ -1,0 +1,200 @@
+// Warp-per-row LayerNorm forward and backward with 128-bit HBM access.
+// Replaces nn.LayerNorm at modeling_vit.py:325-326,333,340 (layernorm_before/after) and :416,455
+// (final layernorm) [a4, a11]. eps comes from ViTConfig.layer_norm_eps (1e-12) and is NOT "fixed".
+// Statistics and the affine transform are fp32 (autocast keeps LayerNorm in fp32);
+// the output is written as bf16 (the operand dtype of the GEMM that consumes it) and/or fp32.
+#include "tic_internal.cuh"
+
+namespace tic {
+namespace {
+
+constexpr int LN_WARPS = 8;
+
+// One warp per row; a lane owns float4 chunks lane, lane + 32, ... (VEC chunks, D = VEC * 128).
+template <int VEC>
+__global__ void __launch_bounds__(LN_WARPS * 32)
+ln_fwd_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ gamma,
+              const float* __restrict__ beta, float eps, int rows, __nv_bfloat16* __restrict__ y_bf16,
+              long long ldy, float* __restrict__ y_f32, long long ldyf, float* __restrict__ mean_out,
+              float* __restrict__ rstd_out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * LN_WARPS + warp;
+  if (row >= rows) return;
+  constexpr int D = VEC * 128;
+  const float4* xr = reinterpret_cast<const float4*>(x + static_cast<long long>(row) * ldx);
+  float4 v[VEC];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    v[i] = xr[lane + 32 * i];
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  const float mean = warp_sum(s) * (1.0f / D);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
+  const float var = warp_sum(q) * (1.0f / D);
+  const float rstd = rsqrtf(var + eps);
+  if (lane == 0) {
+    if (mean_out) mean_out[row] = mean;
+    if (rstd_out) rstd_out[row] = rstd;
+  }
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(beta);
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const float4 g = __ldg(g4 + lane + 32 * i), b = __ldg(b4 + lane + 32 * i);
+    float4 o;
+    o.x = (v[i].x - mean) * rstd * g.x + b.x;
+    o.y = (v[i].y - mean) * rstd * g.y + b.y;
+    o.z = (v[i].z - mean) * rstd * g.z + b.z;
+    o.w = (v[i].w - mean) * rstd * g.w + b.w;
+    if (y_bf16) {
+      uint2 w;
+      w.x = pack_bf16x2(o.x, o.y);
+      w.y = pack_bf16x2(o.z, o.w);
+      reinterpret_cast<uint2*>(y_bf16 + static_cast<long long>(row) * ldy)[lane + 32 * i] = w;
+    }
+    if (y_f32) reinterpret_cast<float4*>(y_f32 + static_cast<long long>(row) * ldyf)[lane + 32 * i] = o;
+  }
+}
+
+// Backward. Per row:  g = dy * gamma;  dx = rstd * (g - mean(g) - xhat * mean(g * xhat)) [+ dres]
+// dgamma += dy * xhat, dbeta += dy are accumulated per lane in registers over the rows this CTA
+// visits, reduced across the CTA's warps through shared memory, then one atomicAdd per column per CTA.
+template <int VEC>
+__global__ void __launch_bounds__(LN_WARPS * 32)
+ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long lddy, const float* __restrict__ x, long long ldx,
+              const float* __restrict__ mean_in, const float* __restrict__ rstd_in, const float* __restrict__ gamma,
+              const float* dres, long long lddres, int rows, float* dx, long long lddx,
+              __nv_bfloat16* __restrict__ dx_bf16, long long lddxb, float* __restrict__ dgamma,
+              float* __restrict__ dbeta) {
+  constexpr int D = VEC * 128;
+  __shared__ float4 red[LN_WARPS][VEC * 32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float4 acc_g[VEC], acc_b[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    acc_g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    acc_b[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  for (int row = blockIdx.x * LN_WARPS + warp; row < rows; row += gridDim.x * LN_WARPS) {
+    const float mean = mean_in[row], rstd = rstd_in[row];
+    const float4* xr = reinterpret_cast<const float4*>(x + static_cast<long long>(row) * ldx);
+    const uint2* dyr = reinterpret_cast<const uint2*>(dy + static_cast<long long>(row) * lddy);
+    float4 xh[VEC], gg[VEC];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const float4 xv = xr[lane + 32 * i];
+      const uint2 dv = dyr[lane + 32 * i];
+      const float4 gm = __ldg(g4 + lane + 32 * i);
+      const float d0 = bf16_lo(dv.x), d1 = bf16_hi(dv.x), d2 = bf16_lo(dv.y), d3 = bf16_hi(dv.y);
+      xh[i].x = (xv.x - mean) * rstd; xh[i].y = (xv.y - mean) * rstd;
+      xh[i].z = (xv.z - mean) * rstd; xh[i].w = (xv.w - mean) * rstd;
+      gg[i].x = d0 * gm.x; gg[i].y = d1 * gm.y; gg[i].z = d2 * gm.z; gg[i].w = d3 * gm.w;
+      s1 += (gg[i].x + gg[i].y) + (gg[i].z + gg[i].w);
+      s2 += (gg[i].x * xh[i].x + gg[i].y * xh[i].y) + (gg[i].z * xh[i].z + gg[i].w * xh[i].w);
+      acc_g[i].x += d0 * xh[i].x; acc_g[i].y += d1 * xh[i].y; acc_g[i].z += d2 * xh[i].z; acc_g[i].w += d3 * xh[i].w;
+      acc_b[i].x += d0; acc_b[i].y += d1; acc_b[i].z += d2; acc_b[i].w += d3;
+    }
+    const float c1 = warp_sum(s1) * (1.0f / D), c2 = warp_sum(s2) * (1.0f / D);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      float4 o;
+      o.x = rstd * (gg[i].x - c1 - xh[i].x * c2);
+      o.y = rstd * (gg[i].y - c1 - xh[i].y * c2);
+      o.z = rstd * (gg[i].z - c1 - xh[i].z * c2);
+      o.w = rstd * (gg[i].w - c1 - xh[i].w * c2);
+      if (dres) {
+        const float4 r = reinterpret_cast<const float4*>(dres + static_cast<long long>(row) * lddres)[lane + 32 * i];
+        o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+      }
+      reinterpret_cast<float4*>(dx + static_cast<long long>(row) * lddx)[lane + 32 * i] = o;
+      if (dx_bf16) {
+        uint2 w;
+        w.x = pack_bf16x2(o.x, o.y);
+        w.y = pack_bf16x2(o.z, o.w);
+        reinterpret_cast<uint2*>(dx_bf16 + static_cast<long long>(row) * lddxb)[lane + 32 * i] = w;
+      }
+    }
+  }
+  // Cross-warp reduction of the parameter gradients, dgamma then dbeta through the same buffer.
+#pragma unroll 1
+  for (int pass = 0; pass < 2; ++pass) {
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) red[warp][lane + 32 * i] = pass == 0 ? acc_g[i] : acc_b[i];
+    __syncthreads();
+    float* dst = pass == 0 ? dgamma : dbeta;
+    if (dst != nullptr) {
+      for (int c = threadIdx.x; c < VEC * 32; c += LN_WARPS * 32) {
+        float4 s = red[0][c];
+#pragma unroll
+        for (int w = 1; w < LN_WARPS; ++w) {
+          const float4 t = red[w][c];
+          s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+        }
+        atomicAdd(dst + 4 * c + 0, s.x);
+        atomicAdd(dst + 4 * c + 1, s.y);
+        atomicAdd(dst + 4 * c + 2, s.z);
+        atomicAdd(dst + 4 * c + 3, s.w);
+      }
+    }
+  }
+}
+
+}  // namespace
+
+int layernorm_fwd(const float* x, long long ldx, const float* gamma, const float* beta, float eps, int rows, int D,
+                  void* y_bf16, long long ldy, float* y_f32, long long ldyf, float* mean, float* rstd,
+                  cudaStream_t stream) {
+  if (rows <= 0) return kOk;
+  if (D % 128 != 0 || D > 1024 * 2) return set_error(kErrUnsupported, "layernorm: D=%d must be a multiple of 128", D);
+  const int grid = (rows + LN_WARPS - 1) / LN_WARPS;
+  auto* yb = reinterpret_cast<__nv_bfloat16*>(y_bf16);
+#define TIC_LN_FWD(V)                                                                                              \
+  case V:                                                                                                          \
+    ln_fwd_kernel<V><<<grid, LN_WARPS * 32, 0, stream>>>(x, ldx, gamma, beta, eps, rows, yb, ldy, y_f32, ldyf, mean, \
+                                                         rstd);                                                    \
+    break;
+  switch (D / 128) {
+    TIC_LN_FWD(1) TIC_LN_FWD(2) TIC_LN_FWD(3) TIC_LN_FWD(4) TIC_LN_FWD(6) TIC_LN_FWD(8) TIC_LN_FWD(10) TIC_LN_FWD(12)
+    TIC_LN_FWD(16)
+    default:
+      return set_error(kErrUnsupported, "layernorm: unsupported D=%d", D);
+  }
+#undef TIC_LN_FWD
+  return check_launch("layernorm_fwd");
+}
+
+int layernorm_bwd(const void* dy_bf16, long long lddy, const float* x, long long ldx, const float* mean,
+                  const float* rstd, const float* gamma, const float* dres, long long lddres, int rows, int D,
+                  float* dx, long long lddx, void* dx_bf16, long long lddxb, float* dgamma, float* dbeta,
+                  cudaStream_t stream) {
+  if (rows <= 0) return kOk;
+  if (D % 128 != 0) return set_error(kErrUnsupported, "layernorm: D=%d must be a multiple of 128", D);
+  int grid = (rows + LN_WARPS - 1) / LN_WARPS;
+  const int max_grid = 148 * 4;
+  if (grid > max_grid) grid = max_grid;
+  auto* dyb = reinterpret_cast<const __nv_bfloat16*>(dy_bf16);
+  auto* dxb = reinterpret_cast<__nv_bfloat16*>(dx_bf16);
+#define TIC_LN_BWD(V)                                                                                             \
+  case V:                                                                                                         \
+    ln_bwd_kernel<V><<<grid, LN_WARPS * 32, 0, stream>>>(dyb, lddy, x, ldx, mean, rstd, gamma, dres, lddres, rows, dx, \
+                                                         lddx, dxb, lddxb, dgamma, dbeta);                        \
+    break;
+  switch (D / 128) {
+    TIC_LN_BWD(1) TIC_LN_BWD(2) TIC_LN_BWD(3) TIC_LN_BWD(4) TIC_LN_BWD(6) TIC_LN_BWD(8)
+    default:
+      return set_error(kErrUnsupported, "layernorm_bwd: unsupported D=%d", D);
+  }
+#undef TIC_LN_BWD
+  return check_launch("layernorm_bwd");
+}
+
+}  // namespace tic

@@ -2,13 +2,80 @@
 #pragma once
 #include "tic_common.cuh"
 
+struct tic_vit_config;
+
 namespace tic {
 
 const char* last_error();
+
+// GEMM epilogues (values are part of the C-ABI: TIC_EPI_* in include/tic_b200.h)
+enum Epilogue : int {
+  kEpiBf16 = 0,         // out bf16 = acc (+bias)
+  kEpiBf16Gelu = 1,     // out2 bf16 = pre = bf16(acc + bias); out bf16 = gelu(pre)
+  kEpiF32Resid = 2,     // out f32 = bf16(acc + bias) + aux_f32[m,n]
+  kEpiBf16DGelu = 3,    // out bf16 = bf16(acc) * gelu'(aux_bf16[m,n])
+  kEpiF32 = 4,          // out f32 = acc (+bias)
+  kEpiF32Atomic = 5,    // out f32 += acc (split-K partial, red.global.add)
+  kEpiF32PosEmbed = 6,  // patch embedding rows: see tic_b200.h
+};
 
 // gemm_tcgen05.cu
 int gemm_bf16(const void* A, long long lda, bool a_mn, const void* B, long long ldb, bool b_mn, int M, int N, int K,
               int epilogue, void* out, long long ldo, void* out2, long long ldo2, const float* bias, const void* aux,
               long long ldaux, int aux_int, int splits, cudaStream_t stream);
+
+// layernorm.cu
+int layernorm_fwd(const float* x, long long ldx, const float* gamma, const float* beta, float eps, int rows, int D,
+                  void* y_bf16, long long ldy, float* y_f32, long long ldyf, float* mean, float* rstd,
+                  cudaStream_t stream);
+int layernorm_bwd(const void* dy_bf16, long long lddy, const float* x, long long ldx, const float* mean,
+                  const float* rstd, const float* gamma, const float* dres, long long lddres, int rows, int D,
+                  float* dx, long long lddx, void* dx_bf16, long long lddxb, float* dgamma, float* dbeta,
+                  cudaStream_t stream);
+
+// elementwise.cu
+int patchify_f32(const float* x, void* out_bf16, int B, int S, cudaStream_t stream);
+int cls_rows(const float* cls, const float* pos, float* x, int B, int N, int D, cudaStream_t stream);
+int embed_bwd(const float* dx, int B, int N, int D, float* dpos, float* dcls, void* dpatch_bf16, cudaStream_t stream);
+int cast_f32_to_bf16(const float* src, void* dst, long long n, cudaStream_t stream);
+int cast_bf16_to_f32(const void* src, float* dst, long long n, cudaStream_t stream);
+int colsum_bf16(const void* dy, long long ld, int rows, int cols, float* out, cudaStream_t stream);
+
+// xent.cu
+int head_fwd(const void* h_bf16, long long ldh, const void* w_bf16, const float* bias, int B, int D, int C,
+             int round_out, float* logits, cudaStream_t stream);
+int head_bwd(const float* dlogits, const void* h_bf16, long long ldh, const void* w_bf16, int B, int D, int C,
+             void* dh_bf16, long long lddh, float* dW, float* db, cudaStream_t stream);
+int softmax_xent(const float* logits, const long long* hard, const float* soft, int B, int C, float grad_scale,
+                 int round_grad, float* loss, float* dlogits, int* correct, cudaStream_t stream);
+
+// adamw.cu
+int adamw_step(float* p, const float* g, float* m, float* v, void* shadow_bf16, long long n, float lr, float beta1,
+               float beta2, float eps, float weight_decay, int step, float grad_scale, cudaStream_t stream);
+
+// attention.cu
+int attention_fwd(const void* q, const void* k, const void* v, long long ld, void* o, long long ldo, float* lse,
+                  int B, int N, int H, int head_dim, float scale, cudaStream_t stream);
+int attention_bwd(const void* q, const void* k, const void* v, long long ld, const void* o, long long ldo,
+                  const void* dout, long long lddo, const float* lse, float* delta, void* dq, void* dk, void* dv,
+                  long long lddqkv, int B, int N, int H, int head_dim, float scale, cudaStream_t stream);
+
+// engine.cu
+struct VitLayout {
+  // element offsets into the parameter arena (fp32, bf16 shadow and gradient arenas share the layout)
+  long long cls, pos, patch_w, patch_b;
+  long long layer0, layer_stride;
+  // per-layer offsets relative to the layer base
+  long long qkv_w, qkv_b, o_w, o_b, fc1_w, fc1_b, fc2_w, fc2_b, ln1_w, ln1_b, ln2_w, ln2_b;
+  long long lnf_w, lnf_b, head_begin, cls_w, cls_b, total;
+};
+int vit_validate(const tic_vit_config* c);
+VitLayout vit_layout(const tic_vit_config* c);
+long long vit_workspace_bytes(const tic_vit_config* c, int B, int training);
+int vit_forward(const tic_vit_config* c, const float* P32, const void* P16, const float* pixels, const void* patches,
+                int B, void* workspace, long long workspace_bytes, int training, float* logits, cudaStream_t st);
+int vit_backward(const tic_vit_config* c, const float* P32, const void* P16, int B, void* workspace,
+                 long long workspace_bytes, const float* dlogits, float* G, int stage_begin, int stage_end,
+                 int head_only, cudaStream_t st);
 
 }  // namespace tic

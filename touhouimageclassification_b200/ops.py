@@ -59,3 +59,96 @@ def gemm_bf16(a, b, *, a_mn_major=False, b_mn_major=False, epilogue=EPI_BF16, bi
     if epilogue == EPI_BF16_GELU:
         return out, out2
     return out
+
+
+def layernorm_fwd(x, gamma, beta, eps, out_bf16=True, out_f32=False):
+    _require_cuda(x, gamma, beta)
+    rows, D = x.shape
+    y = torch.empty((rows, D), device=x.device, dtype=torch.bfloat16) if out_bf16 else None
+    yf = torch.empty((rows, D), device=x.device, dtype=torch.float32) if out_f32 else None
+    mean = torch.empty(rows, device=x.device, dtype=torch.float32)
+    rstd = torch.empty(rows, device=x.device, dtype=torch.float32)
+    _lib.check(_lib.load().tic_layernorm_fwd(_p(x), c_i64(x.stride(0)), _p(gamma), _p(beta), c_float(eps), c_int(rows),
+                                             c_int(D), _p(y), c_i64(D), _p(yf), c_i64(D), _p(mean), _p(rstd), _s()))
+    return y, yf, mean, rstd
+
+
+def layernorm_bwd(dy, x, mean, rstd, gamma, dres=None):
+    _require_cuda(dy, x, mean, rstd, gamma, dres)
+    rows, D = x.shape
+    dx = torch.empty((rows, D), device=x.device, dtype=torch.float32)
+    dxb = torch.empty((rows, D), device=x.device, dtype=torch.bfloat16)
+    dgamma = torch.zeros(D, device=x.device, dtype=torch.float32)
+    dbeta = torch.zeros(D, device=x.device, dtype=torch.float32)
+    _lib.check(_lib.load().tic_layernorm_bwd(_p(dy), c_i64(dy.stride(0)), _p(x), c_i64(x.stride(0)), _p(mean), _p(rstd),
+                                             _p(gamma), _p(dres), c_i64(0 if dres is None else dres.stride(0)),
+                                             c_int(rows), c_int(D), _p(dx), c_i64(D), _p(dxb), c_i64(D), _p(dgamma),
+                                             _p(dbeta), _s()))
+    return dx, dxb, dgamma, dbeta
+
+
+def attention_fwd(qkv, B, N, H, scale=0.125, need_lse=True):
+    """qkv: bf16 [B*N, 3*H*64] (q | k | v column blocks). Returns ctx bf16 [B*N, H*64], lse fp32 [B,H,N]."""
+    _require_cuda(qkv)
+    D = H * 64
+    assert qkv.shape == (B * N, 3 * D) and qkv.dtype == torch.bfloat16 and qkv.is_contiguous()
+    ctx = torch.empty((B * N, D), device=qkv.device, dtype=torch.bfloat16)
+    lse = torch.empty((B, H, N), device=qkv.device, dtype=torch.float32) if need_lse else None
+    base = qkv.data_ptr()
+    _lib.check(_lib.load().tic_attention_fwd(c_void_p(base), c_void_p(base + 2 * D), c_void_p(base + 4 * D), c_i64(3 * D),
+                                             _p(ctx), c_i64(D), _p(lse), c_int(B), c_int(N), c_int(H), c_int(64),
+                                             c_float(scale), _s()))
+    return ctx, lse
+
+
+def attention_bwd(qkv, ctx, dctx, lse, B, N, H, scale=0.125):
+    _require_cuda(qkv, ctx, dctx, lse)
+    D = H * 64
+    dqkv = torch.empty_like(qkv)
+    delta = torch.empty((B, H, N), device=qkv.device, dtype=torch.float32)
+    base, dbase = qkv.data_ptr(), dqkv.data_ptr()
+    _lib.check(_lib.load().tic_attention_bwd(c_void_p(base), c_void_p(base + 2 * D), c_void_p(base + 4 * D), c_i64(3 * D),
+                                             _p(ctx), c_i64(D), _p(dctx), c_i64(D), _p(lse), _p(delta), c_void_p(dbase),
+                                             c_void_p(dbase + 2 * D), c_void_p(dbase + 4 * D), c_i64(3 * D), c_int(B),
+                                             c_int(N), c_int(H), c_int(64), c_float(scale), _s()))
+    return dqkv
+
+
+def softmax_xent(logits, target, grad_scale=None, round_grad=False, need_grad=True):
+    """target: int64 [B] (hard) or float [B,C] (soft). Returns (loss[1], dlogits|None, correct[1] int32)."""
+    _require_cuda(logits, target)
+    B, C = logits.shape
+    logits = logits.float().contiguous()
+    hard = target.dtype in (torch.int64, torch.int32)
+    tgt = target.long().contiguous() if hard else target.float().contiguous()
+    loss = torch.empty(1, device=logits.device, dtype=torch.float32)
+    correct = torch.zeros(1, device=logits.device, dtype=torch.int32)
+    dl = torch.empty_like(logits) if need_grad else None
+    gs = 1.0 / B if grad_scale is None else grad_scale
+    _lib.check(_lib.load().tic_softmax_xent(_p(logits), _p(tgt if hard else None), _p(None if hard else tgt), c_int(B),
+                                            c_int(C), c_float(gs), c_int(int(round_grad)), _p(loss), _p(dl), _p(correct),
+                                            _s()))
+    return loss, dl, correct
+
+
+def adamw_step(p, g, m, v, shadow, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):
+    _require_cuda(p, g, m, v, shadow)
+    _lib.check(_lib.load().tic_adamw_step(_p(p), _p(g), _p(m), _p(v), _p(shadow), c_i64(p.numel()), c_float(lr),
+                                          c_float(beta1), c_float(beta2), c_float(eps), c_float(weight_decay),
+                                          c_int(step), c_float(grad_scale), _s()))
+
+
+def patchify_f32(x):
+    _require_cuda(x)
+    B, C, S, _ = x.shape
+    out = torch.empty((B * (S // 16) ** 2, 768), device=x.device, dtype=torch.bfloat16)
+    _lib.check(_lib.load().tic_patchify_f32(_p(x.contiguous()), _p(out), c_int(B), c_int(S), _s()))
+    return out
+
+
+def colsum_bf16(dy):
+    _require_cuda(dy)
+    rows, cols = dy.shape
+    out = torch.zeros(cols, device=dy.device, dtype=torch.float32)
+    _lib.check(_lib.load().tic_colsum_bf16(_p(dy), c_i64(dy.stride(0)), c_int(rows), c_int(cols), _p(out), _s()))
+    return out
