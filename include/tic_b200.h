@@ -32,6 +32,13 @@ extern "C" {
 /* ---- library ------------------------------------------------------------------------------- */
 TIC_API int tic_abi_version(void);
 TIC_API const char* tic_last_error(void);
+/* Number of kernel launches this library has issued in this process (bench.py's gpu_launches). */
+TIC_API int64_t tic_launch_count(void);
+/* Optional per-launch timing: CUDA events on the launching stream around every kernel while enabled.
+ * tic_prof_collect synchronises and writes "name\tlaunches\ttotal_ms\tflops\tbytes\n" lines (algorithmic
+ * FLOPs / bytes per launch summed per kernel name) into a HOST buffer; returns the bytes written. */
+TIC_API void tic_prof_enable(int on);
+TIC_API int64_t tic_prof_collect(char* buf_host, int64_t buflen);
 
 /* ---- GEMM (tcgen05 / TMEM / TMA) -------------------------------------------------------------
  * D[M,N] = A[M,K] * B[N,K]^T with bf16 operands and fp32 accumulation in tensor memory.

@@ -54,6 +54,7 @@ int adamw_step(float* p, const float* g, float* m, float* v, void* shadow_bf16, 
   if (n == 0) return kOk;
   const double bc1 = 1.0 - pow(static_cast<double>(beta1), step);
   const double bc2 = 1.0 - pow(static_cast<double>(beta2), step);
+  ProfScope prof("adamw", 0.0, static_cast<double>(n) * (shadow_bf16 ? 30 : 28), stream);
   long long grid = (n / 4 + 255) / 256;
   if (grid > 148LL * 8) grid = 148LL * 8;
   adamw_kernel<<<static_cast<int>(grid), 256, 0, stream>>>(p, g, m, v, reinterpret_cast<__nv_bfloat16*>(shadow_bf16),

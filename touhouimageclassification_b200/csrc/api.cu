@@ -12,6 +12,9 @@ extern "C" {
 
 TIC_API int tic_abi_version(void) { return 1; }
 TIC_API const char* tic_last_error(void) { return last_error(); }
+TIC_API int64_t tic_launch_count(void) { return launch_count(); }
+TIC_API void tic_prof_enable(int on) { prof_enable(on != 0); }
+TIC_API int64_t tic_prof_collect(char* buf, int64_t buflen) { return prof_collect(buf, buflen); }
 
 TIC_API int tic_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major,
                           int M, int N, int K, int epilogue, void* out, int64_t ldo, void* out2, int64_t ldo2,

@@ -429,6 +429,7 @@ int attention_fwd(const void* q, const void* k, const void* v, long long ld, voi
   if (head_dim != HD) return set_error(kErrUnsupported, "attention: head_dim=%d (only 64 is supported)", head_dim);
   if (B <= 0 || N <= 0) return kOk;
   dim3 grid((N + TILE - 1) / TILE, H, B);
+  ProfScope prof("attention_fwd", 4.0 * B * H * static_cast<double>(N) * N * HD, 8.0 * B * H * static_cast<double>(N) * HD, stream);
   attn_fwd_kernel<<<grid, 128, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(q),
                                             reinterpret_cast<const __nv_bfloat16*>(k),
                                             reinterpret_cast<const __nv_bfloat16*>(v), ld,
@@ -454,6 +455,7 @@ int attention_bwd(const void* q, const void* k, const void* v, long long ld, con
   auto* ob = reinterpret_cast<const __nv_bfloat16*>(o);
   auto* dob = reinterpret_cast<const __nv_bfloat16*>(dout);
   const long long toks = static_cast<long long>(B) * N;
+  ProfScope prof("attention_bwd", 10.0 * B * H * static_cast<double>(N) * N * HD, 16.0 * B * H * static_cast<double>(N) * HD, stream);
   attn_delta_kernel<<<static_cast<int>((toks + 7) / 8), 256, 0, stream>>>(ob, ldo, dob, lddo, delta, B, N, H);
   int rc = check_launch("attention_delta");
   if (rc) return rc;

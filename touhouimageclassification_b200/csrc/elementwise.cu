@@ -135,6 +135,7 @@ int patchify_f32(const float* x, void* out_bf16, int B, int S, cudaStream_t stre
   if (S % 16 != 0) return set_error(kErrInvalidArg, "patchify: image size %d is not a multiple of 16", S);
   const int G = S / 16;
   const long long total = static_cast<long long>(B) * G * G * 96;
+  ProfScope prof("patchify_f32", 0.0, static_cast<double>(total) * 48, stream);
   patchify_f32_kernel<<<ew_grid(total, 256), 256, 0, stream>>>(x, reinterpret_cast<__nv_bfloat16*>(out_bf16), B, S);
   return check_launch("patchify_f32");
 }
@@ -145,6 +146,7 @@ int cls_rows(const float* cls, const float* pos, float* x, int B, int N, int D, 
 }
 
 int embed_bwd(const float* dx, int B, int N, int D, float* dpos, float* dcls, void* dpatch_bf16, cudaStream_t stream) {
+  ProfScope prof("embed_bwd", 0.0, static_cast<double>(B) * N * D * 6, stream);
   embed_bwd_kernel<<<N, 256, 0, stream>>>(dx, B, N, D, dpos, dcls, reinterpret_cast<__nv_bfloat16*>(dpatch_bf16));
   return check_launch("embed_bwd");
 }
@@ -152,6 +154,7 @@ int embed_bwd(const float* dx, int B, int N, int D, float* dpos, float* dcls, vo
 int cast_f32_to_bf16(const float* src, void* dst, long long n, cudaStream_t stream) {
   if (n % 8 != 0) return set_error(kErrInvalidArg, "cast: n=%lld must be a multiple of 8", n);
   if (n == 0) return kOk;
+  ProfScope prof("cast_f32_to_bf16", 0.0, static_cast<double>(n) * 6, stream);
   cast_f32_bf16_kernel<<<ew_grid(n / 8, 256), 256, 0, stream>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), n / 8);
   return check_launch("cast_f32_to_bf16");
 }
@@ -165,6 +168,7 @@ int cast_bf16_to_f32(const void* src, float* dst, long long n, cudaStream_t stre
 
 int colsum_bf16(const void* dy, long long ld, int rows, int cols, float* out, cudaStream_t stream) {
   if (cols % 8 != 0) return set_error(kErrInvalidArg, "colsum: cols=%d must be a multiple of 8", cols);
+  ProfScope prof("colsum_bf16", 0.0, static_cast<double>(rows) * cols * 2, stream);
   const int gx = (cols + 255) / 256;
   int gy = (148 * 4 + gx - 1) / gx;
   int rows_per_cta = (rows + gy - 1) / gy;

@@ -390,6 +390,15 @@ int gemm_bf16(const void* A, long long lda, bool a_mn, const void* B, long long 
   p.out = out; p.ldo = ldo; p.out2 = out2; p.ldo2 = ldo2;
   p.bias = bias; p.aux = aux; p.ldaux = ldaux; p.aux_int = aux_int;
 
+  static const char* kNames[2][2][7] = {
+      {{"gemm_fwd_bf16", "gemm_fwd_gelu", "gemm_fwd_resid", "gemm_fwd_x", "gemm_fwd_f32", "gemm_fwd_x", "gemm_fwd_posemb"},
+       {"gemm_dgrad_bf16", "gemm_dgrad_x", "gemm_dgrad_x", "gemm_dgrad_dgelu", "gemm_dgrad_f32", "gemm_dgrad_x", "gemm_dgrad_x"}},
+      {{"gemm_x", "gemm_x", "gemm_x", "gemm_x", "gemm_x", "gemm_x", "gemm_x"},
+       {"gemm_wgrad_x", "gemm_wgrad_x", "gemm_wgrad_x", "gemm_wgrad_x", "gemm_wgrad_f32", "gemm_wgrad_atomic", "gemm_wgrad_x"}}};
+  ProfScope prof(epilogue >= 0 && epilogue < 7 ? kNames[a_mn][b_mn][epilogue] : "gemm_x", 2.0 * M * N * K,
+                 2.0 * (static_cast<double>(M) * K + static_cast<double>(N) * K) +
+                     static_cast<double>(M) * N * ((epilogue == kEpiBf16 || epilogue == kEpiBf16DGelu) ? 2 : 4),
+                 stream);
 #define TIC_GEMM_CASE(AMN, BMN, E) \
   if (a_mn == AMN && b_mn == BMN && epilogue == E) return launch<AMN, BMN, E>(ta, tb, p, stream);
   // forward (K-major x K-major)

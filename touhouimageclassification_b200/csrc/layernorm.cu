@@ -156,6 +156,7 @@ int layernorm_fwd(const float* x, long long ldx, const float* gamma, const float
   if (rows <= 0) return kOk;
   if (D % 128 != 0 || D > 1024 * 2) return set_error(kErrUnsupported, "layernorm: D=%d must be a multiple of 128", D);
   const int grid = (rows + LN_WARPS - 1) / LN_WARPS;
+  ProfScope prof("layernorm_fwd", 0.0, static_cast<double>(rows) * D * (4 + (y_bf16 ? 2 : 0) + (y_f32 ? 4 : 0)), stream);
   auto* yb = reinterpret_cast<__nv_bfloat16*>(y_bf16);
 #define TIC_LN_FWD(V)                                                                                              \
   case V:                                                                                                          \
@@ -181,6 +182,7 @@ int layernorm_bwd(const void* dy_bf16, long long lddy, const float* x, long long
   int grid = (rows + LN_WARPS - 1) / LN_WARPS;
   const int max_grid = 148 * 4;
   if (grid > max_grid) grid = max_grid;
+  ProfScope prof("layernorm_bwd", 0.0, static_cast<double>(rows) * D * (2 + 4 + (dres ? 4 : 0) + 4 + (dx_bf16 ? 2 : 0)), stream);
   auto* dyb = reinterpret_cast<const __nv_bfloat16*>(dy_bf16);
   auto* dxb = reinterpret_cast<__nv_bfloat16*>(dx_bf16);
 #define TIC_LN_BWD(V)                                                                                             \

@@ -3,9 +3,13 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <atomic>
+#include <map>
 #include <mutex>
+#include <string>
+#include <vector>
 
-#include "tic_common.cuh"
+#include "tic_internal.cuh"
 
 namespace tic {
 
@@ -36,10 +40,70 @@ int set_error(int code, const char* fmt, ...) {
   return code;
 }
 
+std::atomic<long long> g_launches{0};
+long long launch_count() { return g_launches.load(); }
+
 int check_launch(const char* what) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(kErrCuda, "%s: launch failed: %s", what, cudaGetErrorString(e));
   return kOk;
+}
+
+// ---- per-launch profiling (off by default): CUDA events on the launching stream around every kernel ----
+namespace {
+struct ProfRec { std::string name; double flops, bytes; cudaEvent_t e0, e1; };
+std::mutex g_prof_mu;
+std::vector<ProfRec> g_prof;
+bool g_prof_on = false;
+}  // namespace
+
+void prof_enable(bool on) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (auto& r : g_prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  g_prof.clear();
+  g_prof_on = on;
+}
+
+ProfScope::ProfScope(const char* name, double flops, double bytes, cudaStream_t s) : idx_(-1), stream_(s) {
+  if (!g_prof_on) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  ProfRec r{name, flops, bytes, nullptr, nullptr};
+  cudaEventCreate(&r.e0);
+  cudaEventCreate(&r.e1);
+  cudaEventRecord(r.e0, s);
+  g_prof.push_back(r);
+  idx_ = static_cast<int>(g_prof.size()) - 1;
+}
+ProfScope::~ProfScope() {
+  if (idx_ < 0) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (idx_ < static_cast<int>(g_prof.size())) cudaEventRecord(g_prof[idx_].e1, stream_);
+}
+
+// Writes "name\tlaunches\ttotal_ms\tflops\tbytes\n" per kernel name, in first-launch order. Returns bytes written.
+long long prof_collect(char* buf, long long buflen) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  struct Agg { long long n = 0; double ms = 0, flops = 0, bytes = 0; };
+  std::map<std::string, Agg> agg;
+  std::vector<std::string> order;
+  for (auto& r : g_prof) {
+    cudaEventSynchronize(r.e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r.e0, r.e1);
+    if (!agg.count(r.name)) order.push_back(r.name);
+    Agg& a = agg[r.name];
+    a.n += 1; a.ms += ms; a.flops += r.flops; a.bytes += r.bytes;
+  }
+  long long off = 0;
+  for (auto& name : order) {
+    const Agg& a = agg[name];
+    int n = snprintf(buf + off, off < buflen ? static_cast<size_t>(buflen - off) : 0, "%s\t%lld\t%.6f\t%.6e\t%.6e\n",
+                     name.c_str(), a.n, a.ms, a.flops, a.bytes);
+    if (n < 0 || off + n >= buflen) break;
+    off += n;
+  }
+  return off;
 }
 
 int encode_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t dim0, uint64_t dim1, uint64_t pitch_elems,

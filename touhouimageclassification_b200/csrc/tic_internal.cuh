@@ -7,6 +7,16 @@ struct tic_vit_config;
 namespace tic {
 
 const char* last_error();
+long long launch_count();
+void prof_enable(bool on);
+long long prof_collect(char* buf, long long buflen);
+// RAII: when profiling is enabled, brackets one kernel launch with CUDA events on its stream.
+struct ProfScope {
+  ProfScope(const char* name, double flops, double bytes, cudaStream_t s);
+  ~ProfScope();
+  int idx_;
+  cudaStream_t stream_;
+};
 
 // GEMM epilogues (values are part of the C-ABI: TIC_EPI_* in include/tic_b200.h)
 enum Epilogue : int {

@@ -147,6 +147,7 @@ int head_fwd(const void* h_bf16, long long ldh, const void* w_bf16, const float*
              int round_out, float* logits, cudaStream_t stream) {
   if (D % 8 != 0) return set_error(kErrInvalidArg, "head: D=%d must be a multiple of 8", D);
   if (B <= 0) return kOk;
+  ProfScope prof("head_fwd", 2.0 * B * D * C, 2.0 * (static_cast<double>(B) * D + static_cast<double>(C) * D), stream);
   head_fwd_kernel<<<B, 128, D * 2, stream>>>(reinterpret_cast<const __nv_bfloat16*>(h_bf16), ldh,
                                              reinterpret_cast<const __nv_bfloat16*>(w_bf16), bias, D, C, round_out,
                                              logits);
@@ -156,6 +157,7 @@ int head_fwd(const void* h_bf16, long long ldh, const void* w_bf16, const float*
 int head_bwd(const float* dlogits, const void* h_bf16, long long ldh, const void* w_bf16, int B, int D, int C,
              void* dh_bf16, long long lddh, float* dW, float* db, cudaStream_t stream) {
   if (B <= 0) return kOk;
+  ProfScope prof("head_bwd", 4.0 * B * D * C, 2.0 * (static_cast<double>(B) * D + static_cast<double>(C) * D), stream);
   if (dh_bf16 != nullptr) {
     head_bwd_dh_kernel<<<B, 256, C * 4, stream>>>(dlogits, reinterpret_cast<const __nv_bfloat16*>(w_bf16), D, C,
                                                   reinterpret_cast<__nv_bfloat16*>(dh_bf16), lddh);
@@ -171,6 +173,7 @@ int softmax_xent(const float* logits, const long long* hard, const float* soft, 
   if ((hard == nullptr) == (soft == nullptr))
     return set_error(kErrInvalidArg, "softmax_xent: exactly one of hard/soft targets must be given");
   if (B <= 0) return set_error(kErrInvalidArg, "softmax_xent: empty batch");
+  ProfScope prof("softmax_xent", 0.0, static_cast<double>(B) * C * 8, stream);
   xent_kernel<<<1, 256, 0, stream>>>(logits, hard, soft, B, C, grad_scale, round_grad, loss, dlogits, correct);
   return check_launch("softmax_xent");
 }

@@ -336,9 +336,6 @@ class ViTForImageClassification(nn.Module):
     def _check_input(self, pixel_values: torch.Tensor):
         if not isinstance(pixel_values, torch.Tensor) or pixel_values.dim() != 4:
             raise ValueError("pixel_values must be a [batch, channels, height, width] tensor")
-        if not pixel_values.is_cuda or not self._arena.is_cuda:
-            raise RuntimeError("the B200 ViT runs on CUDA only: move the model and pixel_values to the GPU "
-                               "(there is no CPU fallback)")
         b, ch, h, w = pixel_values.shape
         if ch != self.config.num_channels:
             raise ValueError("Make sure that the channel dimension of the pixel values match with the one set in the "
@@ -346,6 +343,9 @@ class ViTForImageClassification(nn.Module):
         s = self.config.image_size
         if h != s or w != s:
             raise ValueError(f"Input image size ({h}*{w}) doesn't match model ({s}*{s}).")
+        if not pixel_values.is_cuda or not self._arena.is_cuda:
+            raise RuntimeError("the B200 ViT runs on CUDA only: move the model and pixel_values to the GPU "
+                               "(there is no CPU fallback)")
 
     def engine_forward(self, pixel_values=None, patches=None, training=False) -> torch.Tensor:
         """Raw engine forward: fp32 NCHW pixels or bf16 patch rows -> fp32 logits [B, num_labels]."""

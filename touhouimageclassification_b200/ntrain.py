@@ -1,0 +1,114 @@
+"""Mirror of the reference's Lightning module (``TIC/ViT/ntrain.py:16-66`` [a15-a17]).
+
+``ViTLModule`` keeps the constructor signature, the ``vit`` attribute (so Lightning checkpoints carry the
+``vit.<hf key>`` prefix), ``configure_optimizers``, ``training_step`` / ``validation_step`` /
+``test_step`` and the logged metric names. ``lightning`` is not installed in this image; when it is importable
+the class derives from ``lightning.LightningModule``, otherwise from ``torch.nn.Module`` with a ``log`` method
+that records the last values in ``self.logged``.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .finetune import fused_train_step
+from .model import ViT
+from .optim import FusedAdamW
+
+try:  # pragma: no cover - lightning is absent from the build image
+    import lightning as L
+    _Base = L.LightningModule
+except Exception:  # ImportError or a broken install
+    _Base = nn.Module
+
+
+def mixup(x, y, num_classes, lam):
+    """torchvision v2 MixUp (``_augment.py:214-219,249-267``): pair sample i with i-1, blend images and one-hot labels."""
+    yo = F.one_hot(y, num_classes).to(x.dtype) if y.dim() == 1 else y
+    return x.roll(1, 0).mul(1.0 - lam).add_(x.mul(lam)), yo.roll(1, 0).mul(1.0 - lam).add_(yo.mul(lam))
+
+
+def cutmix(x, y, num_classes, lam, r_x, r_y):
+    """torchvision v2 CutMix (``_augment.py:298-337``): paste a box from the rolled batch, labels by box area."""
+    H, W = x.shape[-2:]
+    r = 0.5 * (1.0 - lam) ** 0.5
+    r_w_half, r_h_half = int(r * W), int(r * H)
+    x1, y1 = max(r_x - r_w_half, 0), max(r_y - r_h_half, 0)
+    x2, y2 = min(r_x + r_w_half, W), min(r_y + r_h_half, H)
+    lam_adj = float(1.0 - (x2 - x1) * (y2 - y1) / (W * H))
+    out = x.clone()
+    out[..., y1:y2, x1:x2] = x.roll(1, 0)[..., y1:y2, x1:x2]
+    yo = F.one_hot(y, num_classes).to(x.dtype) if y.dim() == 1 else y
+    return out, yo.roll(1, 0).mul(1.0 - lam_adj).add_(yo.mul(lam_adj))
+
+
+def cutmix_or_mixup(x, y, num_classes):
+    """``v2.RandomChoice([CutMix, MixUp])`` (ntrain.py:30-33): same RNG draws, in the same order, as torchvision."""
+    idx = int(torch.multinomial(torch.tensor([0.5, 0.5]), 1))          # _container.py:152
+    lam = float(torch.distributions.Beta(torch.tensor([1.0]), torch.tensor([1.0])).sample(()))
+    if idx == 0:
+        H, W = x.shape[-2:]
+        r_x = int(torch.randint(W, size=(1,)))
+        r_y = int(torch.randint(H, size=(1,)))
+        return cutmix(x, y, num_classes, lam, r_x, r_y)
+    return mixup(x, y, num_classes, lam)
+
+
+class ViTLModule(_Base):
+    def __init__(self, num_classes: int, pretrained: bool, model_name: str, lr: float, weight_decay: float,
+                 enable_mixup: bool = True, full_finetune: bool = True, fused_optimizer: bool = False):
+        super().__init__()
+        self.num_classes = num_classes
+        self.vit = ViT(num_classes, pretrained, model_name)
+        self.lr = lr
+        self.weight_decay = weight_decay
+        self.enable_mixup = enable_mixup
+        self.fused_optimizer = fused_optimizer
+        self.logged = {}
+        if not full_finetune:
+            for param in self.vit.base_model.parameters():
+                param.requires_grad = False
+
+    if _Base is nn.Module:
+        def log(self, name, value, **kwargs):
+            self.logged[name] = value
+
+    def configure_optimizers(self):
+        if self.fused_optimizer:
+            return FusedAdamW(self.vit, lr=self.lr, weight_decay=self.weight_decay)
+        return torch.optim.AdamW(self.parameters(), lr=self.lr, weight_decay=self.weight_decay)
+
+    def training_step(self, batch, batch_idx):
+        x, y = batch
+        if self.enable_mixup:
+            x, y = cutmix_or_mixup(x, y, self.num_classes)
+        logits = self.vit(x).logits
+        loss = F.cross_entropy(logits.float(), y)
+        self.log('train_loss', loss, prog_bar=True)
+        return loss
+
+    def fused_training_step(self, batch, optimizer: FusedAdamW, grad_sync=None, world_size: int = 1):
+        """training_step + backward + optimizer step in one engine pass (manual-optimization fast path)."""
+        x, y = batch
+        if self.enable_mixup:
+            x, y = cutmix_or_mixup(x, y, self.num_classes)
+        loss = fused_train_step(self.vit, optimizer, x, y, grad_sync=grad_sync, world_size=world_size)
+        self.log('train_loss', loss, prog_bar=True)
+        return loss
+
+    def validation_step(self, batch, batch_idx):
+        x, y = batch
+        logits = self.vit(x).logits
+        loss = F.cross_entropy(logits.float(), y)
+        self.log('val_loss', loss, prog_bar=True)
+        pred = logits.argmax(dim=1)
+        acc = (pred == y).float().mean()
+        self.log('val_acc', acc, prog_bar=True)
+
+    def test_step(self, batch, batch_idx):
+        x, y = batch
+        logits = self.vit(x).logits
+        pred = logits.argmax(dim=1)
+        acc = (pred == y).float().mean()
+        self.log('test_acc', acc, prog_bar=True)
