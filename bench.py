@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: ViT-L/16 224x224 bf16 fine-tune step (BASELINE.json metric), per-GPU batch 256.
+
+  python bench.py --gpus N --steps K --warmup W            # this repo (engine on sm_100a)
+  python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU PyTorch path on the host cores
+
+For N > 1 launch with torchrun (one rank per GPU, NCCL); rank 0 prints ONE JSON line.
+"value" = device-timed images/s with inputs resident in HBM; "e2e" = the same step through the public API
+(finetune.train_step) with pinned host inputs, H2D copies and the loss read-back inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(hidden_size=1024, num_hidden_layers=24, num_attention_heads=16, intermediate_size=4096,
+                image_size=224, num_labels=120)
+PER_GPU_BATCH = 256
+
+
+def flops_per_image_forward(c):
+    N = (c["image_size"] // 16) ** 2 + 1
+    D, L = c["hidden_size"], c["num_hidden_layers"]
+    return L * (24 * N * D * D + 4 * N * N * D) + 2 * (N - 1) * 768 * D + 2 * D * c["num_labels"]
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(source="measured", hbm_gbs=p["hbm_gbs"], bf16_tflops=p["bf16_tflops"],
+                    bf16_tflops_sustained=p.get("bf16_tflops_sustained", p["bf16_tflops"]))
+    return dict(source="fallback", hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0)
+
+
+class ClockSampler:
+    """Samples SM clock / throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join(timeout=2)
+
+    def summary(self):
+        if not self.samples:
+            return dict(sm_mhz=None, sm_max_mhz=self.max_mhz, reasons=sorted(self.reasons))
+        return dict(sm_mhz=statistics.median(self.samples), sm_max_mhz=self.max_mhz, reasons=sorted(self.reasons))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the reference's own PyTorch path on the host cores
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_reference_model():
+    """The class TIC/ViT/model.py:45 instantiates, built from an explicit config (the factory needs the HF hub)."""
+    import torch
+    try:
+        from transformers import ViTConfig, ViTForImageClassification
+        m = ViTForImageClassification(ViTConfig(**WORKLOAD))
+        return m, "reference", "transformers.ViTForImageClassification"
+    except Exception:  # transformers missing: fall back to the oracle port of the same arithmetic
+        from oracle import vit_oracle as O
+        sd = O.deterministic_state_dict(WORKLOAD, 0.02)
+
+        class Port(torch.nn.Module):
+            def __init__(self):
+                super().__init__()
+                self.p = torch.nn.ParameterDict({k.replace(".", "/"): torch.nn.Parameter(v) for k, v in sd.items()})
+
+            def forward(self, x):
+                out = O.vit_forward({k.replace("/", "."): v for k, v in self.p.items()}, x, WORKLOAD["num_attention_heads"])
+                return type("Out", (), {"logits": out})()
+        return Port(), "port", "oracle.vit_oracle.vit_forward"
+
+
+def cpu_train_steps(steps, warmup, time_budget_s, batch=8):
+    """finetune.train_step (finetune.py:54-67) restated for the CPU: zero_grad -> forward -> CrossEntropyLoss ->
+    backward -> AdamW(lr 1e-5, wd 0.01).step() -> loss.item(); fp32, all host threads. Returns img/s + description."""
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(1234)
+    model, kind, what = cpu_reference_model()
+    model.train()
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-5, weight_decay=0.01)
+    crit = torch.nn.CrossEntropyLoss()
+
+    def one(b):
+        x = torch.randn(b, 3, WORKLOAD["image_size"], WORKLOAD["image_size"])
+        y = torch.randint(0, WORKLOAD["num_labels"], (b,))
+        t0 = time.perf_counter()
+        opt.zero_grad()
+        loss = crit(model(x).logits, y)
+        loss.backward()
+        opt.step()
+        loss.item()
+        return time.perf_counter() - t0
+
+    t_first = one(batch)  # also warms the allocator / thread pool
+    # keep the whole run inside the time budget by shrinking the per-step sample
+    while batch > 1 and (steps + warmup) * t_first * 0.8 > time_budget_s:
+        batch //= 2
+        t_first = one(batch)
+    for _ in range(max(0, warmup - 1)):
+        one(batch)
+    times = [one(batch) for _ in range(steps)]
+    ms = statistics.median(times) * 1e3
+    sample = (f"{what} fp32 train step (zero_grad, forward, CrossEntropyLoss, backward, AdamW lr 1e-5 wd 0.01, loss.item) "
+              f"on ViT-L/16 224x224, batch {batch} per step, {steps} timed steps after {warmup} warm-up, median; "
+              f"{cores} host threads")
+    return batch / (ms / 1e3), ms, kind, cores, sample
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    value, ms, kind, cores, sample = cpu_train_steps(args.steps, max(1, args.warmup), time_budget_s=200.0)
+    line = base_line(args, n_gpus=args.gpus)
+    line.update(impl="reference", value=value, ms_per_step=ms, dtype="f32", vs_baseline=None,
+                cpu_baseline=dict(value=value, unit="img/s", cores=cores, kind=kind, sample=sample),
+                e2e=dict(value=value, unit="img/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                gpu_launches=0, roofline=None, clocks=None)
+    print(json.dumps(line), flush=True)
+
+
+def base_line(args, n_gpus):
+    return dict(metric="vit_l16_224_train_images_per_sec", value=None, unit="img/s", n_gpus=n_gpus, steps=args.steps,
+                warmup=args.warmup, ms_per_step=None, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="bf16", data="synthetic",
+                config=dict(workload="ViT-L/16 224x224 bf16 fine-tune step (forward, softmax-CE, backward, AdamW), "
+                                     "random-init weights, synthetic N(0,1) images, int labels",
+                            per_gpu_batch=PER_GPU_BATCH, global_batch=PER_GPU_BATCH * n_gpus, tokens=197,
+                            parallelism=f"dp{n_gpus}", l2_policy="inputs_exceed_l2 (46 GB of activations per step)"))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# own arm
+# ------------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from touhouimageclassification_b200 import _lib
+    from touhouimageclassification_b200.finetune import fused_train_step, train_step
+    from touhouimageclassification_b200.model import ViTConfig, ViTForImageClassification
+    from touhouimageclassification_b200.optim import FusedAdamW
+    from touhouimageclassification_b200.parallel import DataParallelTrainer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("for --gpus N > 1 launch with: python -m torch.distributed.run --nproc-per-node N bench.py ...")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    lib.tic_launch_count.restype = __import__("ctypes").c_int64
+    lib.tic_prof_collect.restype = __import__("ctypes").c_int64
+
+    torch.manual_seed(1234)
+    model = ViTForImageClassification(ViTConfig(**WORKLOAD)).to(dev).train()
+    opt = FusedAdamW(model, lr=1e-5, weight_decay=0.01)
+    trainer = DataParallelTrainer(model, opt)
+    trainer.broadcast_parameters(0)
+    B, S = PER_GPU_BATCH, WORKLOAD["image_size"]
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    x_dev = torch.randn(B, 3, S, S, device=dev, generator=g)
+    y_dev = torch.randint(0, WORKLOAD["num_labels"], (B,), device=dev, generator=g)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    # ---- device-resident throughput
+    for _ in range(max(3, args.warmup)):
+        loss = trainer.step(x_dev, y_dev)
+    barrier()
+    launches0 = lib.tic_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            loss = trainer.step(x_dev, y_dev)
+        e1.record()
+        barrier()
+    launches = lib.tic_launch_count() - launches0
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    ms_step = ms_total / args.steps
+    value = PER_GPU_BATCH * world / (ms_step / 1e3)
+    loss_val = float(loss.item())
+
+    # ---- one extra profiled step: per-kernel CUDA-event durations on the launching stream
+    lib.tic_prof_enable(1)
+    trainer.step(x_dev, y_dev)
+    torch.cuda.synchronize()
+    import ctypes
+    buf = ctypes.create_string_buffer(1 << 16)
+    n = lib.tic_prof_collect(buf, ctypes.c_int64(len(buf)))
+    lib.tic_prof_enable(0)
+    kernels = {}
+    for ln in buf.raw[:n].decode().splitlines():
+        name, cnt, ms, fl, by = ln.split("\t")
+        kernels[name] = dict(launches=int(cnt), ms=float(ms), flops=float(fl), bytes=float(by))
+    gemm = [v for k, v in kernels.items() if k.startswith("gemm_")]
+    gemm_ms = sum(v["ms"] for v in gemm)
+    gemm_flops = sum(v["flops"] for v in gemm)
+    gemm_launches = sum(v["launches"] for v in gemm)
+    prof_ms = sum(v["ms"] for v in kernels.values())
+    peaks = measured_peaks()
+    peak = peaks["bf16_tflops_sustained"]  # kernel timed inside a long step -> sustained figure
+    achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else None
+    step_flops = 3 * flops_per_image_forward(WORKLOAD) * PER_GPU_BATCH
+    roofline = dict(bound="tensor", kernel="gemm_bf16_tcgen05_kernel (all GEMM launches of one step)",
+                    achieved=achieved, peak=peak, unit="TFLOP/s", frac=(achieved / peak if achieved else None),
+                    peak_source=f"{peaks['source']} bf16_tflops_sustained (burst {peaks['bf16_tflops']})",
+                    traffic=None, launches_per_step=gemm_launches, kernel_ms_per_step=gemm_ms,
+                    kernel_share_of_step=gemm_ms / prof_ms if prof_ms else None,
+                    step_achieved=step_flops / (ms_step / 1e3) / 1e12,
+                    step_frac_of_burst=step_flops / (ms_step / 1e3) / 1e12 / peaks["bf16_tflops"],
+                    breakdown_ms={k: round(v["ms"], 3) for k, v in sorted(kernels.items(), key=lambda kv: -kv[1]["ms"])})
+
+    # ---- end to end through the public API: pinned host tensors -> finetune.train_step -> loss.item()
+    x_host = torch.randn(B, 3, S, S).pin_memory()
+    y_host = torch.randint(0, WORKLOAD["num_labels"], (B,)).pin_memory()
+    crit = torch.nn.CrossEntropyLoss()
+
+    def e2e_step():
+        if world > 1:
+            opt.zero_grad()
+            xi = x_host.to(dev, non_blocking=True)
+            yi = y_host.to(dev, non_blocking=True)
+            return float(trainer.step(xi, yi).item())
+        return train_step(model, (x_host, y_host), opt, crit, None)
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / e2e_steps
+    e2e = dict(value=PER_GPU_BATCH * world / (e2e_ms / 1e3), unit="img/s", ms_per_step=e2e_ms,
+               h2d_bytes_per_step=(x_host.numel() * 4 + y_host.numel() * 8) * world, d2h_bytes_per_step=4 * world,
+               api="touhouimageclassification_b200.finetune.train_step(model, (x_host, y_host), FusedAdamW, CrossEntropyLoss)")
+
+    if rank == 0:
+        line = base_line(args, n_gpus=world)
+        line.update(value=value, ms_per_step=ms_step, e2e=e2e, roofline=roofline, gpu_launches=int(launches),
+                    clocks=clocks.summary(), loss=loss_val)
+        if world == 1 and not args.no_cpu_baseline:
+            v, ms, kind, cores, sample = cpu_train_steps(steps=2, warmup=1, time_budget_s=60.0)
+            line["cpu_baseline"] = dict(value=v, unit="img/s", cores=cores, kind=kind, sample=sample)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

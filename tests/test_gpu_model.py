@@ -100,6 +100,8 @@ def test_fused_step_equals_autograd_step_and_oracle():
         lb = train_step(b, (x, y), opt_b, crit, None)
         assert abs(la - lb) < 5e-3
     for (n, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters()):
+        if "key.bias" in n:  # gradient is pure rounding noise (mathematically zero): AdamW turns it into +-lr steps
+            continue
         # first AdamW steps move by ~lr*sign(g): allow sign flips on noise-level gradients only
         d = (pa - pb).abs()
         assert d.max().item() <= 3 * 3e-3, n

@@ -32,7 +32,9 @@ def fused_train_step(model: ViTForImageClassification, optimizer: FusedAdamW, in
     batch = inputs.shape[0] if inputs is not None else patches.shape[0] // ((model.config.image_size // 16) ** 2)
     logits = model.engine_forward(inputs, patches=patches, training=True)
     loss, dlogits, _ = ops.softmax_xent(logits, target, grad_scale=1.0 / (batch * world_size), round_grad=True)
-    model.grad_arena().zero_()
+    if not optimizer.arena_clean:
+        model.grad_arena().zero_()
+    optimizer.arena_clean = False
     params = model._params_in_order()
     head_only = not any(p.requires_grad for p in params[:-2])
     if grad_sync is None:

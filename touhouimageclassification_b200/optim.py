@@ -44,6 +44,7 @@ class FusedAdamW(torch.optim.Optimizer):
         self._ranges = None
         self._arena_ptr = None
         self.grads_in_arena = False  # set by the fused train step: gradients already live in the grad arena
+        self.arena_clean = False     # True right after zero_grad(): the fused step need not zero the arena again
 
     # ---- arenas -----------------------------------------------------------------------------------
     def _ensure_state(self):
@@ -86,6 +87,7 @@ class FusedAdamW(torch.optim.Optimizer):
                     p.grad.zero_()
         self.model.grad_arena().zero_()
         self.grads_in_arena = False
+        self.arena_clean = True
 
     def _gather_grads(self):
         """Generic path (``loss.backward()``): make sure every .grad is inside the gradient arena."""
@@ -123,6 +125,7 @@ class FusedAdamW(torch.optim.Optimizer):
                 st["step"].fill_(float(self._step))
         model.mark_shadow_fresh()
         self.grads_in_arena = False
+        self.arena_clean = False
         return loss
 
     def load_state_dict(self, state_dict):
