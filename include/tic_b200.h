@@ -123,6 +123,23 @@ TIC_API int tic_cast_bf16_to_f32(const void* src_bf16, float* dst, int64_t n, vo
 /* out[n] += sum_m dy[m, n] (bias gradients) */
 TIC_API int tic_colsum_bf16(const void* dy_bf16, int64_t ld, int rows, int cols, float* out_accum, void* stream);
 
+/* ---- fused augment + normalize + patchify ------------------------------------------------------------
+ * Replaces the per-sample CPU torchvision pipeline of AugmentedDataset.setup (ntrain.py:104-112 [a18]) and the
+ * im2col of the patch projection: RandomResizedCrop(size) -> HFlip -> ColorJitter(.2,.2,.2,.1, random order) ->
+ * RandomGrayscale(.2) -> RandomErasing(.5, value 0) -> ToTensor -> Normalize(mean, std) -> bf16 patch rows.
+ * tic_augment_sample_params (HOST code) fills, per sample, ints[16] = {top, left, h, w, flip, op0..op3, gray,
+ * erase_i, erase_j, erase_h, erase_w, jitter_on, 0} and floats[4] = {brightness, contrast, saturation, hue} from a
+ * counter-based RNG keyed by (seed, first_sample + b); recipe 0 = full, 1 = crop + flip + erase only
+ * (ntrain.py:127-134). tic_augment_patchify: images uint8 NHWC [B,H,W,3] (device), ints/floats on the DEVICE,
+ * patches bf16 [B*(size/16)^2, 768] with K ordered (c, py, px); pixels_out (optional, may be NULL) receives the
+ * uint8 NHWC image after erasing. size must be a multiple of 16 and <= 224. Results are bit-exact against
+ * oracle/augment_oracle.py. */
+TIC_API int tic_augment_sample_params(int64_t seed, int64_t first_sample, int B, int H, int W, int size, int recipe,
+                                      int32_t* ints_host, float* floats_host);
+TIC_API int tic_augment_patchify(const void* images_u8, int B, int H, int W, const int32_t* ints, const float* floats,
+                                 int size, const float* mean3_host, const float* std3_host, void* patches_bf16,
+                                 void* pixels_out_u8, void* stream);
+
 /* ---- whole-model engine ---------------------------------------------------------------------------
  * Stands where ViTForImageClassification.forward (modeling_vit.py:620-653) and its autograd backward
  * stand in the reference [a2-a12]. Parameters live in one fp32 arena whose element offsets are reported

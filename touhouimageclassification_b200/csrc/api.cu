@@ -81,6 +81,17 @@ TIC_API int tic_colsum_bf16(const void* dy_bf16, int64_t ld, int rows, int cols,
   return colsum_bf16(dy_bf16, ld, rows, cols, out_accum, S(stream));
 }
 
+TIC_API int tic_augment_sample_params(int64_t seed, int64_t first_sample, int B, int H, int W, int size, int recipe,
+                                      int32_t* ints_host, float* floats_host) {
+  return augment_sample_params(seed, first_sample, B, H, W, size, recipe, ints_host, floats_host);
+}
+TIC_API int tic_augment_patchify(const void* images_u8, int B, int H, int W, const int32_t* ints, const float* floats,
+                                 int size, const float* mean3_host, const float* std3_host, void* patches_bf16,
+                                 void* pixels_out_u8, void* stream) {
+  return augment_patchify(images_u8, B, H, W, ints, floats, size, mean3_host, std3_host, patches_bf16, pixels_out_u8,
+                          S(stream));
+}
+
 TIC_API int64_t tic_vit_param_arena_elems(const tic_vit_config* cfg) {
   if (vit_validate(cfg) != kOk) return -1;
   return vit_layout(cfg).total;

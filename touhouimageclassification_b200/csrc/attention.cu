@@ -68,12 +68,15 @@ TIC_DEVINL void load_a_frags(uint32_t tile, int warp_row0, int lane, uint32_t (&
 }
 
 // acc[j][*] (16 x 64, 8 n-tiles) = A(16 x 64) * T^T where T is a swizzled [64 rows (n)][64 (k)] tile.
-TIC_DEVINL void mma_a_tT(float (&acc)[8][4], const uint32_t (&a)[4][4], uint32_t tile, int lane) {
+// Only the first `n_valid` rows of T hold real data: 16-row groups past it are skipped (warp-uniform).
+template <bool FULL>
+TIC_DEVINL void mma_a_tT_impl(float (&acc)[8][4], const uint32_t (&a)[4][4], uint32_t tile, int lane, int n_valid) {
   const int mi = lane >> 3, r = lane & 7;
 #pragma unroll
   for (int kk = 0; kk < 4; ++kk) {
 #pragma unroll
     for (int jp = 0; jp < 4; ++jp) {
+      if (!FULL && 16 * jp >= n_valid) continue;
       uint32_t b0, b1, b2, b3;
       ldsm_x4(tile + tile_off(8 * (2 * jp + (mi >> 1)) + r, 2 * kk + (mi & 1)), b0, b1, b2, b3);
       mma16816(acc[2 * jp], a[kk], b0, b1);
@@ -82,11 +85,19 @@ TIC_DEVINL void mma_a_tT(float (&acc)[8][4], const uint32_t (&a)[4][4], uint32_t
   }
 }
 
+TIC_DEVINL void mma_a_tT(float (&acc)[8][4], const uint32_t (&a)[4][4], uint32_t tile, int lane, int n_valid) {
+  if (n_valid >= TILE) mma_a_tT_impl<true>(acc, a, tile, lane, n_valid);   // branch-free fast path for full tiles
+  else mma_a_tT_impl<false>(acc, a, tile, lane, n_valid);
+}
+
 // acc[j][*] (16 x 64) += P(16 x 64, given as fp32 C-fragments, rounded to bf16) * T, T = swizzled [64 (k)][64 (n)].
-TIC_DEVINL void mma_p_t(float (&acc)[8][4], const float (&p)[8][4], uint32_t tile, int lane) {
+// Only the first `k_valid` rows of T (and columns of P) are non-zero: later 16-wide k-steps are skipped.
+template <bool FULL>
+TIC_DEVINL void mma_p_t_impl(float (&acc)[8][4], const float (&p)[8][4], uint32_t tile, int lane, int k_valid) {
   const int mi = lane >> 3, r = lane & 7;
 #pragma unroll
   for (int kk = 0; kk < 4; ++kk) {
+    if (!FULL && 16 * kk >= k_valid) continue;
     uint32_t a[4];
     a[0] = pack_bf16x2(p[2 * kk][0], p[2 * kk][1]);
     a[1] = pack_bf16x2(p[2 * kk][2], p[2 * kk][3]);
@@ -100,6 +111,11 @@ TIC_DEVINL void mma_p_t(float (&acc)[8][4], const float (&p)[8][4], uint32_t til
       mma16816(acc[2 * jp + 1], a, b2, b3);
     }
   }
+}
+
+TIC_DEVINL void mma_p_t(float (&acc)[8][4], const float (&p)[8][4], uint32_t tile, int lane, int k_valid) {
+  if (k_valid >= TILE) mma_p_t_impl<true>(acc, p, tile, lane, k_valid);
+  else mma_p_t_impl<false>(acc, p, tile, lane, k_valid);
 }
 
 // Stage a warp's 16 x 64 fp32 C-fragments as bf16 into its rows of a swizzled tile, then store them
@@ -150,6 +166,7 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __rest
 
   const int nkv = (N + TILE - 1) / TILE;
   const float c2 = scale * LOG2E;
+  const bool warp_active = q0 + warp * 16 < N;
   uint32_t qa[4][4];
   float oacc[8][4];
 #pragma unroll
@@ -169,11 +186,16 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __rest
     }
     __syncthreads();
     if (kb == 0) load_a_frags(sQ, warp * 16, lane, qa);
+    const int kv_valid = min(TILE, N - kb * TILE);
+    if (!warp_active) {  // all 16 query rows of this warp are padding: only take part in the tile pipeline
+      __syncthreads();
+      continue;
+    }
 
     float s[8][4];
 #pragma unroll
     for (int j = 0; j < 8; ++j) s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
-    mma_a_tT(s, qa, sK + buf * TILE_BYTES, lane);
+    mma_a_tT(s, qa, sK + buf * TILE_BYTES, lane, kv_valid);
 
     const int kbase = kb * TILE;
     const bool tail = kbase + TILE > N;
@@ -206,9 +228,10 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __rest
     }
     l0 = l0 * a0 + r0;
     l1 = l1 * a1 + r1;
-    mma_p_t(oacc, s, sV + buf * TILE_BYTES, lane);
+    mma_p_t(oacc, s, sV + buf * TILE_BYTES, lane, kv_valid);
     __syncthreads();
   }
+  if (!warp_active) return;
   l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
   l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
   const int g = lane >> 2;
@@ -281,6 +304,7 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __r
   const float D0 = r0i < N ? drow[r0i] : 0.f, D1 = r1i < N ? drow[r1i] : 0.f;
   const float c2 = scale * LOG2E;
   const int nkv = (N + TILE - 1) / TILE;
+  const bool warp_active = q0 + warp * 16 < N;
   uint32_t qa[4][4], da[4][4];
   float acc[8][4];
 #pragma unroll
@@ -301,14 +325,19 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __r
       load_a_frags(sQ, warp * 16, lane, qa);
       load_a_frags(sDO, warp * 16, lane, da);
     }
+    const int kv_valid = min(TILE, N - kb * TILE);
+    if (!warp_active) {
+      __syncthreads();
+      continue;
+    }
     float s[8][4], dp[8][4];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
       dp[j][0] = dp[j][1] = dp[j][2] = dp[j][3] = 0.f;
     }
-    mma_a_tT(s, qa, sK + buf * TILE_BYTES, lane);
-    mma_a_tT(dp, da, sV + buf * TILE_BYTES, lane);
+    mma_a_tT(s, qa, sK + buf * TILE_BYTES, lane, kv_valid);
+    mma_a_tT(dp, da, sV + buf * TILE_BYTES, lane, kv_valid);
     const int kbase = kb * TILE;
     const bool tail = kbase + TILE > N;
 #pragma unroll
@@ -320,9 +349,10 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __r
         s[j][e] = p * (dp[j][e] - (e < 2 ? D0 : D1));
       }
     }
-    mma_p_t(acc, s, sK + buf * TILE_BYTES, lane);
+    mma_p_t(acc, s, sK + buf * TILE_BYTES, lane, kv_valid);
     __syncthreads();
   }
+  if (!warp_active) return;
   store_c_tile(sQ, smem, acc, scale, scale, warp * 16, lane, dq + tok0 * lddq + h * HD, lddq, q0, N);
 }
 
@@ -361,6 +391,7 @@ attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __
   const int t = lane & 3;
   const float c2 = scale * LOG2E;
   const int nq = (N + TILE - 1) / TILE;
+  const bool warp_active = k0 + warp * 16 < N;
   uint32_t ka[4][4], va[4][4];
   float dkacc[8][4], dvacc[8][4];
 #pragma unroll
@@ -389,14 +420,19 @@ attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __
       load_a_frags(sK, warp * 16, lane, ka);
       load_a_frags(sV, warp * 16, lane, va);
     }
+    const int q_valid = min(TILE, N - qb * TILE);
+    if (!warp_active) {
+      __syncthreads();
+      continue;
+    }
     float s[8][4], dp[8][4];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
       dp[j][0] = dp[j][1] = dp[j][2] = dp[j][3] = 0.f;
     }
-    mma_a_tT(s, ka, sQ + buf * TILE_BYTES, lane);    // S^T[key, query]
-    mma_a_tT(dp, va, sDO + buf * TILE_BYTES, lane);  // dP^T[key, query]
+    mma_a_tT(s, ka, sQ + buf * TILE_BYTES, lane, q_valid);    // S^T[key, query]
+    mma_a_tT(dp, va, sDO + buf * TILE_BYTES, lane, q_valid);  // dP^T[key, query]
     const float* Lb = sL + buf * TILE;
     const float* Db = sD + buf * TILE;
     float ds[8][4];
@@ -411,10 +447,11 @@ attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __
         ds[j][e] = p * (dp[j][e] - ((e & 1) ? Dq.y : Dq.x));
       }
     }
-    mma_p_t(dvacc, s, sDO + buf * TILE_BYTES, lane);  // dV += P^T dO
-    mma_p_t(dkacc, ds, sQ + buf * TILE_BYTES, lane);  // dK += dS^T Q
+    mma_p_t(dvacc, s, sDO + buf * TILE_BYTES, lane, q_valid);  // dV += P^T dO
+    mma_p_t(dkacc, ds, sQ + buf * TILE_BYTES, lane, q_valid);  // dK += dS^T Q
     __syncthreads();
   }
+  if (!warp_active) return;
   store_c_tile(sK, smem, dkacc, scale, scale, warp * 16, lane, dk + tok0 * lddkv + h * HD, lddkv, k0, N);
   store_c_tile(sV, smem + TILE_BYTES, dvacc, 1.f, 1.f, warp * 16, lane, dv + tok0 * lddkv + h * HD, lddkv, k0, N);
 }

@@ -1,0 +1,348 @@
+// Fused augment + normalize + patchify: uint8 NHWC thumbnails -> bf16 patch tokens [B*196, 768] in one launch,
+// replacing the reference's per-sample CPU/PIL torchvision pipeline (AugmentedDataset.setup,
+// $REF/TIC/ViT/ntrain.py:104-112 [a18]) and the Conv2d im2col that follows it (modeling_vit.py:151,166 [a2]):
+//   RandomResizedCrop(224) -> HFlip -> ColorJitter (random order) -> RandomGrayscale -> RandomErasing(value 0)
+//   -> ToTensor -> Normalize -> 16x16 patch rows.
+// Per-sample parameters (crop box, flip, jitter order + factors, gray flag, erase box) are sampled on the host from
+// a counter-based hash RNG (augment_sample_params below; torchvision's sampling rules, v2/_geometry.py:272-308,
+// v2/_color.py:146-171, v2/_augment.py:100-136) so a CPU restatement consumes the same integers.
+// The arithmetic contract is bit-exactness against that restatement (oracle/augment_oracle.py): every float32
+// operation below is an explicitly rounded intrinsic (__fmul_rn / __fadd_rn / __fdiv_rn), never a fused multiply-add.
+//
+// One CTA per image. The 224x224x3 uint8 working image lives in shared memory (planar, 147 KB), so the colour ops,
+// which need a whole-image mean for the contrast step, never round-trip through HBM.
+// Algorithmic HBM traffic per image: <= H*W*3 bytes read (the crop), 196*768*2 = 301056 bytes written.
+#include <cmath>
+
+#include "tic_internal.cuh"
+
+namespace tic {
+namespace {
+
+constexpr int AUG_THREADS = 512;
+constexpr int AUG_MAX_TAPS = 8;
+constexpr int AUG_MAX_SIZE = 224;
+
+struct AugTables {
+  int lo[2][AUG_MAX_SIZE];
+  int n[2][AUG_MAX_SIZE];
+  float w[2][AUG_MAX_SIZE][AUG_MAX_TAPS];
+};
+
+__device__ __forceinline__ float gray_floor_f(float r, float g, float b) {
+  // floor(0.2989 r + 0.587 g + 0.114 b), products and sums separately rounded
+  return floorf(__fadd_rn(__fadd_rn(__fmul_rn(r, 0.2989f), __fmul_rn(g, 0.587f)), __fmul_rn(b, 0.114f)));
+}
+__device__ __forceinline__ unsigned char to_u8(float x) {  // clamp to [0, 255] then truncate
+  return static_cast<unsigned char>(fminf(fmaxf(x, 0.0f), 255.0f));
+}
+__device__ __forceinline__ float clamp01(float x) { return fminf(fmaxf(x, 0.0f), 1.0f); }
+
+__global__ void __launch_bounds__(AUG_THREADS, 1)
+augment_patchify_kernel(const unsigned char* __restrict__ images, int H, int W, const int* __restrict__ ints,
+                        const float* __restrict__ floats, int size, float m0, float m1, float m2, float s0, float s1,
+                        float s2, __nv_bfloat16* __restrict__ patches, unsigned char* __restrict__ pixels_out) {
+  extern __shared__ __align__(16) unsigned char aug_smem[];
+  AugTables* tab = reinterpret_cast<AugTables*>(aug_smem);
+  unsigned char* pix = aug_smem + ((sizeof(AugTables) + 15) / 16) * 16;  // planar [3][size*size]
+  __shared__ int gray_sum;
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int* pi = ints + b * 16;
+  const float* pf = floats + b * 4;
+  const int top = pi[0], left = pi[1], ch = pi[2], cw = pi[3], flip = pi[4];
+  const int npix = size * size;
+  const unsigned char* src = images + static_cast<long long>(b) * H * W * 3;
+  if (tid == 0) gray_sum = 0;
+
+  // ---- 1. antialiased-bilinear tap tables (x: dir 0 over crop width, y: dir 1 over crop height)
+  for (int e = tid; e < 2 * size; e += AUG_THREADS) {
+    const int dir = e / size, o = e - dir * size;
+    const int in = dir == 0 ? cw : ch;
+    const float scale = __fdiv_rn(static_cast<float>(in), static_cast<float>(size));
+    const float fs = fmaxf(scale, 1.0f);
+    const float center = __fmul_rn(__fadd_rn(static_cast<float>(o), 0.5f), scale);
+    int a = static_cast<int>(__fadd_rn(__fsub_rn(center, fs), 0.5f));
+    int e2 = static_cast<int>(__fadd_rn(__fadd_rn(center, fs), 0.5f));
+    a = max(a, 0);
+    e2 = min(e2, in);
+    const int cnt = min(e2 - a, AUG_MAX_TAPS);
+    float raw[AUG_MAX_TAPS];
+    float total = 0.0f;
+#pragma unroll
+    for (int k = 0; k < AUG_MAX_TAPS; ++k) {
+      float wk = 0.0f;
+      if (k < cnt) {
+        const float x = __fdiv_rn(__fadd_rn(__fsub_rn(static_cast<float>(a + k), center), 0.5f), fs);
+        wk = fmaxf(0.0f, __fsub_rn(1.0f, fabsf(x)));
+        total = __fadd_rn(total, wk);
+      }
+      raw[k] = wk;
+    }
+#pragma unroll
+    for (int k = 0; k < AUG_MAX_TAPS; ++k) tab->w[dir][o][k] = k < cnt ? __fdiv_rn(raw[k], total) : 0.0f;
+    tab->lo[dir][o] = a;
+    tab->n[dir][o] = cnt;
+  }
+  __syncthreads();
+
+  // ---- 2. resized crop (+ horizontal flip) -> uint8 working image in shared memory
+  for (int p = tid; p < npix; p += AUG_THREADS) {
+    const int yo = p / size, xo = p - yo * size;
+    const int xr = flip ? size - 1 - xo : xo;
+    const int lox = tab->lo[0][xr], nx = tab->n[0][xr], loy = tab->lo[1][yo], ny = tab->n[1][yo];
+    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
+    for (int ty = 0; ty < ny; ++ty) {
+      const unsigned char* row = src + (static_cast<long long>(top + loy + ty) * W + left + lox) * 3;
+      float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+      for (int tx = 0; tx < nx; ++tx) {
+        const float wx = tab->w[0][xr][tx];
+        r0 = __fadd_rn(r0, __fmul_rn(static_cast<float>(__ldg(row + 3 * tx + 0)), wx));
+        r1 = __fadd_rn(r1, __fmul_rn(static_cast<float>(__ldg(row + 3 * tx + 1)), wx));
+        r2 = __fadd_rn(r2, __fmul_rn(static_cast<float>(__ldg(row + 3 * tx + 2)), wx));
+      }
+      const float wy = tab->w[1][yo][ty];
+      acc0 = __fadd_rn(acc0, __fmul_rn(r0, wy));
+      acc1 = __fadd_rn(acc1, __fmul_rn(r1, wy));
+      acc2 = __fadd_rn(acc2, __fmul_rn(r2, wy));
+    }
+    pix[p] = to_u8(floorf(__fadd_rn(acc0, 0.5f)));
+    pix[npix + p] = to_u8(floorf(__fadd_rn(acc1, 0.5f)));
+    pix[2 * npix + p] = to_u8(floorf(__fadd_rn(acc2, 0.5f)));
+  }
+  // each thread keeps working on its own pixels: no barrier needed until the contrast mean
+
+  // ---- 3. ColorJitter in the sampled order (torchvision tensor kernels on uint8 images)
+  if (pi[14]) {
+    for (int k = 0; k < 4; ++k) {
+      const int op = pi[5 + k];
+      if (op == 0) {  // brightness: clamp(x * b)
+        const float f = pf[0];
+        for (int p = tid; p < npix; p += AUG_THREADS) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) pix[c * npix + p] = to_u8(__fmul_rn(static_cast<float>(pix[c * npix + p]), f));
+        }
+      } else if (op == 1) {  // contrast: blend(x, mean(gray), c)
+        int local = 0;
+        for (int p = tid; p < npix; p += AUG_THREADS)
+          local += static_cast<int>(gray_floor_f(pix[p], pix[npix + p], pix[2 * npix + p]));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+        if ((tid & 31) == 0) atomicAdd(&gray_sum, local);
+        __syncthreads();
+        const float mean = __fdiv_rn(static_cast<float>(gray_sum), static_cast<float>(npix));
+        const float f = pf[1], omf = __fsub_rn(1.0f, f);
+        const float mterm = __fmul_rn(mean, omf);
+        for (int p = tid; p < npix; p += AUG_THREADS) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+            pix[c * npix + p] = to_u8(__fadd_rn(__fmul_rn(static_cast<float>(pix[c * npix + p]), f), mterm));
+        }
+      } else if (op == 2) {  // saturation: blend(x, gray(x), s)
+        const float f = pf[2], omf = __fsub_rn(1.0f, f);
+        for (int p = tid; p < npix; p += AUG_THREADS) {
+          const float r = pix[p], g = pix[npix + p], bl = pix[2 * npix + p];
+          const float gterm = __fmul_rn(gray_floor_f(r, g, bl), omf);
+          pix[p] = to_u8(__fadd_rn(__fmul_rn(r, f), gterm));
+          pix[npix + p] = to_u8(__fadd_rn(__fmul_rn(g, f), gterm));
+          pix[2 * npix + p] = to_u8(__fadd_rn(__fmul_rn(bl, f), gterm));
+        }
+      } else {  // hue: RGB -> HSV, shift h, HSV -> RGB (v2/functional/_color.py:300-400)
+        const float hf = pf[3];
+        for (int p = tid; p < npix; p += AUG_THREADS) {
+          const float inv255 = 0.00392156862745098f;
+          const float r = __fmul_rn(static_cast<float>(pix[p]), inv255);
+          const float g = __fmul_rn(static_cast<float>(pix[npix + p]), inv255);
+          const float bl = __fmul_rn(static_cast<float>(pix[2 * npix + p]), inv255);
+          const float maxc = fmaxf(fmaxf(r, g), bl), minc = fminf(fminf(r, g), bl);
+          const bool eqc = maxc == minc;
+          const float cr = __fsub_rn(maxc, minc);
+          const float s = __fdiv_rn(cr, eqc ? 1.0f : maxc);
+          const float dv = eqc ? 1.0f : cr;
+          const float rc = __fdiv_rn(__fsub_rn(maxc, r), dv), gc = __fdiv_rn(__fsub_rn(maxc, g), dv),
+                      bc = __fdiv_rn(__fsub_rn(maxc, bl), dv);
+          const bool neq_r = maxc != r, eq_g = maxc == g;
+          const float hg = __fmul_rn(__fsub_rn(__fadd_rn(rc, 2.0f), bc), (eq_g && neq_r) ? 1.0f : 0.0f);
+          const float hr = __fmul_rn(__fsub_rn(bc, gc), neq_r ? 0.0f : 1.0f);
+          const float hb = __fmul_rn(__fsub_rn(__fadd_rn(gc, 4.0f), rc), (neq_r && !eq_g) ? 1.0f : 0.0f);
+          float h = __fadd_rn(__fadd_rn(hr, hg), hb);
+          h = fmodf(__fadd_rn(__fmul_rn(h, 0.16666666666666666f), 1.0f), 1.0f);
+          h = fmodf(__fadd_rn(h, hf), 1.0f);
+          if (h < 0.0f) h = __fadd_rn(h, 1.0f);
+          const float v = maxc;
+          const float h6 = __fmul_rn(h, 6.0f);
+          const float fi = floorf(h6);
+          const float f = __fsub_rn(h6, fi);
+          const int i = static_cast<int>(fi) % 6;
+          const float sxf = __fmul_rn(s, f);
+          const float oms = __fsub_rn(1.0f, s);
+          const float q = clamp01(__fmul_rn(__fsub_rn(1.0f, sxf), v));
+          const float t = clamp01(__fmul_rn(__fadd_rn(sxf, oms), v));
+          const float pp = clamp01(__fmul_rn(oms, v));
+          float ro, go, bo;
+          switch (i) {
+            case 0: ro = v; go = t; bo = pp; break;
+            case 1: ro = q; go = v; bo = pp; break;
+            case 2: ro = pp; go = v; bo = t; break;
+            case 3: ro = pp; go = q; bo = v; break;
+            case 4: ro = t; go = pp; bo = v; break;
+            default: ro = v; go = pp; bo = q; break;
+          }
+          pix[p] = static_cast<unsigned char>(__fmul_rn(ro, 255.999f));
+          pix[npix + p] = static_cast<unsigned char>(__fmul_rn(go, 255.999f));
+          pix[2 * npix + p] = static_cast<unsigned char>(__fmul_rn(bo, 255.999f));
+        }
+      }
+    }
+  }
+
+  // ---- 4. RandomGrayscale, RandomErasing (value 0, before normalisation)
+  const int gray = pi[9], ei = pi[10], ej = pi[11], eh = pi[12], ew = pi[13];
+  if (gray || (eh > 0 && ew > 0) || pixels_out != nullptr) {
+    for (int p = tid; p < npix; p += AUG_THREADS) {
+      unsigned char r = pix[p], g = pix[npix + p], bl = pix[2 * npix + p];
+      if (gray) r = g = bl = static_cast<unsigned char>(gray_floor_f(r, g, bl));
+      const int y = p / size, x = p - y * size;
+      if (y >= ei && y < ei + eh && x >= ej && x < ej + ew) r = g = bl = 0;
+      pix[p] = r; pix[npix + p] = g; pix[2 * npix + p] = bl;
+      if (pixels_out != nullptr) {
+        unsigned char* o = pixels_out + (static_cast<long long>(b) * npix + p) * 3;
+        o[0] = r; o[1] = g; o[2] = bl;
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- 5. ToTensor (/255), Normalize, bf16, patch rows with K ordered (c, py, px); 16-byte stores
+  const int G = size / 16;
+  const float mean_c[3] = {m0, m1, m2}, std_c[3] = {s0, s1, s2};
+  __nv_bfloat16* out = patches + static_cast<long long>(b) * G * G * 768;
+  for (int e = tid; e < G * G * 96; e += AUG_THREADS) {
+    const int row = e / 96, chunk = e - row * 96;
+    const int k = chunk * 8;
+    const int c = k >> 8, py = (k & 255) >> 4, px = k & 15;
+    const int gy = row / G, gx = row - gy * G;
+    const unsigned char* sp = pix + c * npix + (gy * 16 + py) * size + gx * 16 + px;
+    const uint2 raw = *reinterpret_cast<const uint2*>(sp);
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const unsigned int byte = ((j < 4 ? raw.x : raw.y) >> (8 * (j & 3))) & 0xffu;
+      v[j] = __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(byte), 255.0f), mean_c[c]), std_c[c]);
+    }
+    uint4 w;
+    w.x = pack_bf16x2(v[0], v[1]); w.y = pack_bf16x2(v[2], v[3]);
+    w.z = pack_bf16x2(v[4], v[5]); w.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(out + static_cast<long long>(row) * 768 + k) = w;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- host sampler
+inline uint32_t rng_u32(uint64_t seed, uint64_t sample, uint64_t draw) {
+  uint64_t z = seed * 0x9E3779B97F4A7C15ull + sample * 0xBF58476D1CE4E5B9ull + draw * 0x94D049BB133111EBull +
+               0x2545F4914F6CDD1Dull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z = z ^ (z >> 31);
+  return static_cast<uint32_t>(z >> 32);
+}
+struct Stream {
+  uint64_t seed, sample, draw;
+  double uniform(double lo, double hi) {
+    const double u = static_cast<double>(rng_u32(seed, sample, draw++) >> 8) * (1.0 / 16777216.0);
+    return lo + (hi - lo) * u;
+  }
+  int randint(int n) { return static_cast<int>(rng_u32(seed, sample, draw++) % static_cast<uint32_t>(n)); }
+};
+inline int round_half_even(double x) { return static_cast<int>(std::nearbyint(x)); }  // == Python round()
+
+}  // namespace
+
+// recipe: 0 = full (ntrain.py:104-112), 1 = generalization only (crop + flip + erase, ntrain.py:127-134)
+int augment_sample_params(long long seed, long long first_sample, int B, int H, int W, int size, int recipe,
+                          int* ints_host, float* floats_host) {
+  if (B < 0 || H <= 0 || W <= 0 || size <= 0) return set_error(kErrInvalidArg, "augment_sample_params: bad sizes");
+  for (int b = 0; b < B; ++b) {
+    Stream st{static_cast<uint64_t>(seed), static_cast<uint64_t>(first_sample + b), 0};
+    int* I = ints_host + 16 * b;
+    float* F = floats_host + 4 * b;
+    const double area = static_cast<double>(H) * W;
+    const double lr0 = std::log(3.0 / 4.0), lr1 = std::log(4.0 / 3.0);
+    int top = 0, left = 0, h = H, w = W;
+    bool found = false;
+    for (int t = 0; t < 10 && !found; ++t) {
+      const double target = area * st.uniform(0.08, 1.0);
+      const double aspect = std::exp(st.uniform(lr0, lr1));
+      const int cw = round_half_even(std::sqrt(target * aspect));
+      const int chh = round_half_even(std::sqrt(target / aspect));
+      if (0 < cw && cw <= W && 0 < chh && chh <= H) {
+        top = st.randint(H - chh + 1);
+        left = st.randint(W - cw + 1);
+        h = chh; w = cw;
+        found = true;
+      }
+    }
+    if (!found) {
+      const double in_ratio = static_cast<double>(W) / static_cast<double>(H);
+      if (in_ratio < 3.0 / 4.0) { w = W; h = round_half_even(w / (3.0 / 4.0)); }
+      else if (in_ratio > 4.0 / 3.0) { h = H; w = round_half_even(h * (4.0 / 3.0)); }
+      else { w = W; h = H; }
+      top = (H - h) / 2; left = (W - w) / 2;
+    }
+    const int flip = st.uniform(0.0, 1.0) < 0.5 ? 1 : 0;
+    int perm[4] = {0, 1, 2, 3};
+    for (int i = 3; i > 0; --i) {
+      const int j = st.randint(i + 1);
+      const int tmp = perm[i]; perm[i] = perm[j]; perm[j] = tmp;
+    }
+    const double bb = st.uniform(0.8, 1.2), cc = st.uniform(0.8, 1.2), ss = st.uniform(0.8, 1.2), hh = st.uniform(-0.1, 0.1);
+    int gray = st.uniform(0.0, 1.0) < 0.2 ? 1 : 0;
+    int ei = 0, ej = 0, eh = 0, ew = 0;
+    if (st.uniform(0.0, 1.0) < 0.5) {
+      const double el0 = std::log(0.3), el1 = std::log(3.3);
+      for (int t = 0; t < 10; ++t) {
+        const double ea = static_cast<double>(size) * size * st.uniform(0.02, 0.33);
+        const double aspect = std::exp(st.uniform(el0, el1));
+        const int rh = round_half_even(std::sqrt(ea * aspect));
+        const int rw = round_half_even(std::sqrt(ea / aspect));
+        if (!(rh < size && rw < size)) continue;
+        ei = st.randint(size - rh + 1);
+        ej = st.randint(size - rw + 1);
+        eh = rh; ew = rw;
+        break;
+      }
+    }
+    int jitter_on = 1;
+    if (recipe == 1) { jitter_on = 0; gray = 0; }
+    const int vals[16] = {top, left, h, w, flip, perm[0], perm[1], perm[2], perm[3], gray, ei, ej, eh, ew, jitter_on, 0};
+    for (int i = 0; i < 16; ++i) I[i] = vals[i];
+    F[0] = static_cast<float>(bb); F[1] = static_cast<float>(cc); F[2] = static_cast<float>(ss); F[3] = static_cast<float>(hh);
+  }
+  return kOk;
+}
+
+int augment_patchify(const void* images_u8, int B, int H, int W, const int* ints_dev, const float* floats_dev, int size,
+                     const float* mean3_host, const float* std3_host, void* patches_bf16, void* pixels_out_u8,
+                     cudaStream_t stream) {
+  if (size % 16 != 0 || size > AUG_MAX_SIZE || size <= 0)
+    return set_error(kErrUnsupported, "augment_patchify: output size %d (multiple of 16, <= %d)", size, AUG_MAX_SIZE);
+  if (B <= 0) return kOk;
+  // tap tables hold at most AUG_MAX_TAPS taps: support = max(in/out, 1) must be <= 3.5
+  if (H > 3 * size || W > 3 * size)
+    return set_error(kErrUnsupported, "augment_patchify: source %dx%d is more than 3x the output size", H, W);
+  const int smem = static_cast<int>((sizeof(AugTables) + 15) / 16 * 16) + 3 * size * size;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(augment_patchify_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>((sizeof(AugTables) + 15) / 16 * 16) + 3 * AUG_MAX_SIZE * AUG_MAX_SIZE);
+    if (e != cudaSuccess) return set_error(kErrCuda, "augment_patchify: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  ProfScope prof("augment_patchify", 0.0, static_cast<double>(B) * (static_cast<double>(H) * W * 3 + (size / 16) * (size / 16) * 768.0 * 2), stream);
+  augment_patchify_kernel<<<B, AUG_THREADS, smem, stream>>>(
+      reinterpret_cast<const unsigned char*>(images_u8), H, W, ints_dev, floats_dev, size, mean3_host[0], mean3_host[1],
+      mean3_host[2], std3_host[0], std3_host[1], std3_host[2], reinterpret_cast<__nv_bfloat16*>(patches_bf16),
+      reinterpret_cast<unsigned char*>(pixels_out_u8));
+  return check_launch("augment_patchify");
+}
+
+}  // namespace tic

@@ -36,7 +36,8 @@ constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_THREADS = (NUM_EPI_WARPS + 2) * 32;
 constexpr int TMEM_COLS = ACC_STAGES * BN;  // 512
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int EPI_STAGE_BYTES = 32 * 32 * 4;  // per epilogue warp: 32 rows x 32 fp32 columns
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + NUM_EPI_WARPS * EPI_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 
 
 struct GemmParams {
@@ -61,7 +62,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint8_t* smem_stage = smem + STAGES * STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_stage + NUM_EPI_WARPS * EPI_STAGE_BYTES);
   uint64_t* full_bar = bars;                      // [STAGES]   TMA -> MMA
   uint64_t* empty_bar = bars + STAGES;            // [STAGES]   MMA -> TMA
   uint64_t* tmem_full_bar = bars + 2 * STAGES;    // [ACC_STAGES] MMA -> epilogue
@@ -177,8 +179,16 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps
+    // Phase A: TMEM -> registers (one accumulator row per thread) -> this warp's 32x32 fp32 staging tile in
+    //          shared memory (16-byte chunks XOR-swizzled by row, conflict-free both ways).
+    // Phase B: read the tile back transposed so that a warp instruction covers 4 rows x 128 contiguous bytes;
+    //          all epilogue math and every global access (bias, residual, pre-activation, outputs) happens
+    //          here with fully coalesced 128-bit (fp32) / 64-bit (bf16) accesses.
     const int quad = warp & 3;   // TMEM lane quadrant this warp may access
     const int half = warp >> 2;  // which 128-column half of the accumulator
+    uint8_t* stg = smem_stage + warp * EPI_STAGE_BYTES;
+    const int sub_row = lane >> 3;  // phase B: row within a group of 4
+    const int ch = lane & 7;        // phase B: 16-byte chunk (4 fp32 columns)
     int acc_stage = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -186,130 +196,99 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       const int rem = tile - split * tiles_per_split;
       const int m_idx = (rem / n_blocks) * BM;
       const int n_idx = (rem % n_blocks) * BN;
-      const bool has_k = split * k_blocks_per_split < k_blocks_total;
       mbar_wait(&tmem_full_bar[acc_stage], acc_phase);
       tc_fence_after();
-      const int row = m_idx + quad * 32 + lane;
-      const bool row_ok = row < p.M;
+      const int row_base = m_idx + quad * 32;
 #pragma unroll 1
       for (int c = 0; c < BN / 2 / 32; ++c) {
         const int col0 = n_idx + half * (BN / 2) + c * 32;
-        uint32_t r[32];
-        const uint32_t taddr = tmem_base + acc_stage * BN + half * (BN / 2) + c * 32 + (static_cast<uint32_t>(quad * 32) << 16);
-        tmem_ld_32x32b_x32(taddr, r);
-        tmem_ld_wait();
-        if (!row_ok || col0 >= p.N || !has_k) continue;
-        float v[32];
+        const int col = col0 + ch * 4;
+        // Issue this chunk's coalesced auxiliary loads (residual / pre-activation / pos-emb rows) before the
+        // TMEM load so that their latency overlaps phase A.
+        float4 auxf[8];
+        uint2 auxh[8];
+        if constexpr (EPI == kEpiF32Resid || EPI == kEpiF32PosEmbed || EPI == kEpiBf16DGelu) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-        if constexpr (EPI != kEpiF32Atomic && EPI != kEpiBf16DGelu) {
-          if (p.bias != nullptr) {
-            const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float4 b = __ldg(b4 + i);
-              v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+          for (int i = 0; i < 8; ++i) {
+            const int row = row_base + 4 * i + sub_row;
+            if (row < p.M && col < p.N) {
+              if constexpr (EPI == kEpiF32Resid) {
+                auxf[i] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.aux) +
+                                                           static_cast<long long>(row) * p.ldaux + col);
+              } else if constexpr (EPI == kEpiF32PosEmbed) {
+                const int pidx = row % p.aux_int;
+                auxf[i] = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.aux) +
+                                                                static_cast<long long>(1 + pidx) * p.ldaux + col));
+              } else {
+                auxh[i] = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.aux) +
+                                                               static_cast<long long>(row) * p.ldaux + col));
+              }
             }
           }
         }
-        // Columns are handled in groups of 8; N % 8 == 0 is enforced on the host.
-        const int ngroups = min(4, (p.N - col0) >> 3);
-        if constexpr (EPI == kEpiBf16) {
-          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<long long>(row) * p.ldo + col0;
+        {
+          uint32_t r[32];
+          const uint32_t taddr = tmem_base + acc_stage * BN + half * (BN / 2) + c * 32 + (static_cast<uint32_t>(quad * 32) << 16);
+          tmem_ld_32x32b_x32(taddr, r);
+          tmem_ld_wait();
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            if (g < ngroups) {
-              uint4 w;
-              w.x = pack_bf16x2(v[8 * g + 0], v[8 * g + 1]); w.y = pack_bf16x2(v[8 * g + 2], v[8 * g + 3]);
-              w.z = pack_bf16x2(v[8 * g + 4], v[8 * g + 5]); w.w = pack_bf16x2(v[8 * g + 6], v[8 * g + 7]);
-              *reinterpret_cast<uint4*>(o + 8 * g) = w;
-            }
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+        }
+        __syncwarp();
+        if (col < p.N) {
+          float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
+          if constexpr (EPI != kEpiF32Atomic && EPI != kEpiBf16DGelu) {
+            if (p.bias != nullptr) bias = __ldg(reinterpret_cast<const float4*>(p.bias + col));
           }
-        } else if constexpr (EPI == kEpiBf16Gelu) {
-          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<long long>(row) * p.ldo + col0;
-          __nv_bfloat16* o2 = reinterpret_cast<__nv_bfloat16*>(p.out2) + static_cast<long long>(row) * p.ldo2 + col0;
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            if (g < ngroups) {
-              uint4 w, a;
-              uint32_t* wp = &w.x;
-              uint32_t* ap = &a.x;
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                // The reference evaluates GELU on the bf16-rounded fc1 output (autocast).
-                const uint32_t pre = pack_bf16x2(v[8 * g + 2 * j], v[8 * g + 2 * j + 1]);
-                wp[j] = pre;
-                ap[j] = pack_bf16x2(gelu_erf(bf16_lo(pre)), gelu_erf(bf16_hi(pre)));
-              }
-              if (p.out2 != nullptr) *reinterpret_cast<uint4*>(o2 + 8 * g) = w;
-              *reinterpret_cast<uint4*>(o + 8 * g) = a;
-            }
-          }
-        } else if constexpr (EPI == kEpiBf16DGelu) {
-          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<long long>(row) * p.ldo + col0;
-          const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(p.aux) + static_cast<long long>(row) * p.ldaux + col0;
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            if (g < ngroups) {
-              const uint4 pre = __ldg(reinterpret_cast<const uint4*>(x + 8 * g));
-              const uint32_t* pp = &pre.x;
-              uint4 w;
-              uint32_t* wp = &w.x;
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float g0 = round_bf16(v[8 * g + 2 * j]), g1 = round_bf16(v[8 * g + 2 * j + 1]);
-                wp[j] = pack_bf16x2(g0 * gelu_erf_grad(bf16_lo(pp[j])), g1 * gelu_erf_grad(bf16_hi(pp[j])));
-              }
-              *reinterpret_cast<uint4*>(o + 8 * g) = w;
-            }
-          }
-        } else if constexpr (EPI == kEpiF32Resid) {
-          float* o = reinterpret_cast<float*>(p.out) + static_cast<long long>(row) * p.ldo + col0;
-          const float* x = reinterpret_cast<const float*>(p.aux) + static_cast<long long>(row) * p.ldaux + col0;
-#pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            if (g < 2 * ngroups) {
+          for (int i = 0; i < 8; ++i) {
+            const int rr = 4 * i + sub_row;
+            const int row = row_base + rr;
+            if (row >= p.M) continue;
+            float4 a = *reinterpret_cast<const float4*>(stg + rr * 128 + ((ch ^ (rr & 7)) << 4));
+            a.x += bias.x; a.y += bias.y; a.z += bias.z; a.w += bias.w;
+            if constexpr (EPI == kEpiBf16) {
+              __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<long long>(row) * p.ldo + col;
+              *reinterpret_cast<uint2*>(o) = make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
+            } else if constexpr (EPI == kEpiBf16Gelu) {
+              // The reference evaluates GELU on the bf16-rounded fc1 output (autocast).
+              const uint32_t p0 = pack_bf16x2(a.x, a.y), p1 = pack_bf16x2(a.z, a.w);
+              if (p.out2 != nullptr)
+                *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out2) + static_cast<long long>(row) * p.ldo2 + col) =
+                    make_uint2(p0, p1);
+              *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<long long>(row) * p.ldo + col) =
+                  make_uint2(pack_bf16x2(gelu_fast(bf16_lo(p0)), gelu_fast(bf16_hi(p0))),
+                             pack_bf16x2(gelu_fast(bf16_lo(p1)), gelu_fast(bf16_hi(p1))));
+            } else if constexpr (EPI == kEpiBf16DGelu) {
+              const uint2 pre = auxh[i];
+              const float g0 = round_bf16(a.x), g1 = round_bf16(a.y), g2 = round_bf16(a.z), g3 = round_bf16(a.w);
+              *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<long long>(row) * p.ldo + col) =
+                  make_uint2(pack_bf16x2(g0 * gelu_grad_fast(bf16_lo(pre.x)), g1 * gelu_grad_fast(bf16_hi(pre.x))),
+                             pack_bf16x2(g2 * gelu_grad_fast(bf16_lo(pre.y)), g3 * gelu_grad_fast(bf16_hi(pre.y))));
+            } else if constexpr (EPI == kEpiF32Resid) {
               // bf16 GEMM output added to the fp32 residual stream (Appendix B).
-              const float4 a = *reinterpret_cast<const float4*>(x + 4 * g);
-              float4 w;
-              w.x = round_bf16(v[4 * g + 0]) + a.x; w.y = round_bf16(v[4 * g + 1]) + a.y;
-              w.z = round_bf16(v[4 * g + 2]) + a.z; w.w = round_bf16(v[4 * g + 3]) + a.w;
-              *reinterpret_cast<float4*>(o + 4 * g) = w;
-            }
-          }
-        } else if constexpr (EPI == kEpiF32) {
-          float* o = reinterpret_cast<float*>(p.out) + static_cast<long long>(row) * p.ldo + col0;
-#pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            if (g < 2 * ngroups)
-              *reinterpret_cast<float4*>(o + 4 * g) = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
-          }
-        } else if constexpr (EPI == kEpiF32Atomic) {
-          float* o = reinterpret_cast<float*>(p.out) + static_cast<long long>(row) * p.ldo + col0;
-#pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            if (g < 2 * ngroups) {
-              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + 4 * g), "f"(v[4 * g]),
-                           "f"(v[4 * g + 1]), "f"(v[4 * g + 2]), "f"(v[4 * g + 3])
+              const float4 x = auxf[i];
+              *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<long long>(row) * p.ldo + col) =
+                  make_float4(round_bf16(a.x) + x.x, round_bf16(a.y) + x.y, round_bf16(a.z) + x.z, round_bf16(a.w) + x.w);
+            } else if constexpr (EPI == kEpiF32) {
+              *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<long long>(row) * p.ldo + col) = a;
+            } else if constexpr (EPI == kEpiF32Atomic) {
+              float* o = reinterpret_cast<float*>(p.out) + static_cast<long long>(row) * p.ldo + col;
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w)
                            : "memory");
-            }
-          }
-        } else if constexpr (EPI == kEpiF32PosEmbed) {
-          const int P = p.aux_int;
-          const int img = row / P, pidx = row - img * P;
-          float* o = reinterpret_cast<float*>(p.out) + (static_cast<long long>(img) * (P + 1) + 1 + pidx) * p.ldo + col0;
-          const float* x = reinterpret_cast<const float*>(p.aux) + static_cast<long long>(1 + pidx) * p.ldaux + col0;
-#pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            if (g < 2 * ngroups) {
-              const float4 a = __ldg(reinterpret_cast<const float4*>(x + 4 * g));
-              float4 w;
-              w.x = round_bf16(v[4 * g + 0]) + a.x; w.y = round_bf16(v[4 * g + 1]) + a.y;
-              w.z = round_bf16(v[4 * g + 2]) + a.z; w.w = round_bf16(v[4 * g + 3]) + a.w;
-              *reinterpret_cast<float4*>(o + 4 * g) = w;
+            } else if constexpr (EPI == kEpiF32PosEmbed) {
+              const int P = p.aux_int;
+              const int img = row / P, pidx = row - img * P;
+              const float4 x = auxf[i];
+              *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) +
+                                         (static_cast<long long>(img) * (P + 1) + 1 + pidx) * p.ldo + col) =
+                  make_float4(round_bf16(a.x) + x.x, round_bf16(a.y) + x.y, round_bf16(a.z) + x.z, round_bf16(a.w) + x.w);
             }
           }
         }
+        __syncwarp();
       }
       // All TMEM reads of this warp have completed (wait::ld above): hand the accumulator stage back.
       tc_fence_before();

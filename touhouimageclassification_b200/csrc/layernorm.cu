@@ -63,8 +63,9 @@ ln_fwd_kernel(const float* __restrict__ x, long long ldx, const float* __restric
 }
 
 // Backward. Per row:  g = dy * gamma;  dx = rstd * (g - mean(g) - xhat * mean(g * xhat)) [+ dres]
-// dgamma += dy * xhat, dbeta += dy are accumulated per lane in registers over the rows this CTA
-// visits, reduced across the CTA's warps through shared memory, then one atomicAdd per column per CTA.
+// dgamma += dy * xhat and dbeta += dy are accumulated over the rows a warp visits in a per-warp slice of
+// shared memory (keeps the register count low enough for 3 CTAs / SM), reduced across the CTA's warps at
+// the end, then one atomicAdd per column per CTA.
 template <int VEC>
 __global__ void __launch_bounds__(LN_WARPS * 32)
 ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long lddy, const float* __restrict__ x, long long ldx,
@@ -73,13 +74,16 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long lddy, const float*
               __nv_bfloat16* __restrict__ dx_bf16, long long lddxb, float* __restrict__ dgamma,
               float* __restrict__ dbeta) {
   constexpr int D = VEC * 128;
-  __shared__ float4 red[LN_WARPS][VEC * 32];
+  extern __shared__ float4 ln_smem[];
+  float4* sg = ln_smem;                           // [LN_WARPS][VEC * 32] dgamma partials
+  float4* sb = ln_smem + LN_WARPS * VEC * 32;     // [LN_WARPS][VEC * 32] dbeta partials
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float4 acc_g[VEC], acc_b[VEC];
+  float4* my_g = sg + warp * VEC * 32;
+  float4* my_b = sb + warp * VEC * 32;
 #pragma unroll
   for (int i = 0; i < VEC; ++i) {
-    acc_g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    acc_b[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    my_g[lane + 32 * i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    my_b[lane + 32 * i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   const float4* g4 = reinterpret_cast<const float4*>(gamma);
   for (int row = blockIdx.x * LN_WARPS + warp; row < rows; row += gridDim.x * LN_WARPS) {
@@ -99,8 +103,11 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long lddy, const float*
       gg[i].x = d0 * gm.x; gg[i].y = d1 * gm.y; gg[i].z = d2 * gm.z; gg[i].w = d3 * gm.w;
       s1 += (gg[i].x + gg[i].y) + (gg[i].z + gg[i].w);
       s2 += (gg[i].x * xh[i].x + gg[i].y * xh[i].y) + (gg[i].z * xh[i].z + gg[i].w * xh[i].w);
-      acc_g[i].x += d0 * xh[i].x; acc_g[i].y += d1 * xh[i].y; acc_g[i].z += d2 * xh[i].z; acc_g[i].w += d3 * xh[i].w;
-      acc_b[i].x += d0; acc_b[i].y += d1; acc_b[i].z += d2; acc_b[i].w += d3;
+      float4 ag = my_g[lane + 32 * i], ab = my_b[lane + 32 * i];
+      ag.x += d0 * xh[i].x; ag.y += d1 * xh[i].y; ag.z += d2 * xh[i].z; ag.w += d3 * xh[i].w;
+      ab.x += d0; ab.y += d1; ab.z += d2; ab.w += d3;
+      my_g[lane + 32 * i] = ag;
+      my_b[lane + 32 * i] = ab;
     }
     const float c1 = warp_sum(s1) * (1.0f / D), c2 = warp_sum(s2) * (1.0f / D);
 #pragma unroll
@@ -123,27 +130,22 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long lddy, const float*
       }
     }
   }
-  // Cross-warp reduction of the parameter gradients, dgamma then dbeta through the same buffer.
-#pragma unroll 1
-  for (int pass = 0; pass < 2; ++pass) {
-    __syncthreads();
+  __syncthreads();
+  for (int c = threadIdx.x; c < VEC * 32; c += LN_WARPS * 32) {
+    float4 s = sg[c], t = sb[c];
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) red[warp][lane + 32 * i] = pass == 0 ? acc_g[i] : acc_b[i];
-    __syncthreads();
-    float* dst = pass == 0 ? dgamma : dbeta;
-    if (dst != nullptr) {
-      for (int c = threadIdx.x; c < VEC * 32; c += LN_WARPS * 32) {
-        float4 s = red[0][c];
-#pragma unroll
-        for (int w = 1; w < LN_WARPS; ++w) {
-          const float4 t = red[w][c];
-          s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
-        }
-        atomicAdd(dst + 4 * c + 0, s.x);
-        atomicAdd(dst + 4 * c + 1, s.y);
-        atomicAdd(dst + 4 * c + 2, s.z);
-        atomicAdd(dst + 4 * c + 3, s.w);
-      }
+    for (int w = 1; w < LN_WARPS; ++w) {
+      const float4 a = sg[w * VEC * 32 + c], b = sb[w * VEC * 32 + c];
+      s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+      t.x += b.x; t.y += b.y; t.z += b.z; t.w += b.w;
+    }
+    if (dgamma != nullptr) {
+      atomicAdd(dgamma + 4 * c + 0, s.x); atomicAdd(dgamma + 4 * c + 1, s.y);
+      atomicAdd(dgamma + 4 * c + 2, s.z); atomicAdd(dgamma + 4 * c + 3, s.w);
+    }
+    if (dbeta != nullptr) {
+      atomicAdd(dbeta + 4 * c + 0, t.x); atomicAdd(dbeta + 4 * c + 1, t.y);
+      atomicAdd(dbeta + 4 * c + 2, t.z); atomicAdd(dbeta + 4 * c + 3, t.w);
     }
   }
 }
@@ -180,16 +182,23 @@ int layernorm_bwd(const void* dy_bf16, long long lddy, const float* x, long long
   if (rows <= 0) return kOk;
   if (D % 128 != 0) return set_error(kErrUnsupported, "layernorm: D=%d must be a multiple of 128", D);
   int grid = (rows + LN_WARPS - 1) / LN_WARPS;
-  const int max_grid = 148 * 4;
+  const int max_grid = 148 * 3;
   if (grid > max_grid) grid = max_grid;
   ProfScope prof("layernorm_bwd", 0.0, static_cast<double>(rows) * D * (2 + 4 + (dres ? 4 : 0) + 4 + (dx_bf16 ? 2 : 0)), stream);
   auto* dyb = reinterpret_cast<const __nv_bfloat16*>(dy_bf16);
   auto* dxb = reinterpret_cast<__nv_bfloat16*>(dx_bf16);
 #define TIC_LN_BWD(V)                                                                                             \
-  case V:                                                                                                         \
-    ln_bwd_kernel<V><<<grid, LN_WARPS * 32, 0, stream>>>(dyb, lddy, x, ldx, mean, rstd, gamma, dres, lddres, rows, dx, \
-                                                         lddx, dxb, lddxb, dgamma, dbeta);                        \
-    break;
+  case V: {                                                                                                       \
+    const int smem = 2 * LN_WARPS * V * 32 * 16;                                                                  \
+    static bool attr_set = false;                                                                                 \
+    if (!attr_set && smem > 48 * 1024) {                                                                          \
+      cudaFuncSetAttribute(ln_bwd_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);                  \
+      attr_set = true;                                                                                            \
+    }                                                                                                             \
+    ln_bwd_kernel<V><<<grid, LN_WARPS * 32, smem, stream>>>(dyb, lddy, x, ldx, mean, rstd, gamma, dres, lddres, rows, \
+                                                            dx, lddx, dxb, lddxb, dgamma, dbeta);                 \
+    break;                                                                                                        \
+  }
   switch (D / 128) {
     TIC_LN_BWD(1) TIC_LN_BWD(2) TIC_LN_BWD(3) TIC_LN_BWD(4) TIC_LN_BWD(6) TIC_LN_BWD(8)
     default:

@@ -43,6 +43,31 @@ TIC_DEVINL float gelu_erf_grad(float x) {
   const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
   return cdf + x * pdf;
 }
+// Same functions for the GEMM epilogues, whose results are rounded to bf16: erfc via Abramowitz-Stegun 7.1.26
+// (|error| < 1.5e-7, far below bf16 resolution) with one MUFU.RCP + one MUFU.EX2 shared by cdf and pdf.
+//   half_erfc = 0.5 * erfc(|x| / sqrt(2)) = 0.5 * t * (a1 + t (a2 + t (a3 + t (a4 + t a5)))) * exp(-x^2 / 2)
+TIC_DEVINL void gelu_parts(float x, float& cdf, float& e) {
+  const float u = fabsf(x) * 0.70710678118654752440f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, u, 1.0f)));
+  e = exp2f(x * x * -0.72134752044448170368f);  // exp(-x^2 / 2)
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(t, poly, 1.421413741f);
+  poly = fmaf(t, poly, -0.284496736f);
+  poly = fmaf(t, poly, 0.254829592f);
+  const float half_erfc = 0.5f * t * poly * e;
+  cdf = x >= 0.f ? 1.0f - half_erfc : half_erfc;
+}
+TIC_DEVINL float gelu_fast(float x) {
+  float cdf, e;
+  gelu_parts(x, cdf, e);
+  return x * cdf;
+}
+TIC_DEVINL float gelu_grad_fast(float x) {
+  float cdf, e;
+  gelu_parts(x, cdf, e);
+  return fmaf(x * 0.39894228040143267794f, e, cdf);
+}
 
 TIC_DEVINL float warp_sum(float v) {
 #pragma unroll

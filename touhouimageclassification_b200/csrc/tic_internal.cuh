@@ -70,6 +70,13 @@ int attention_bwd(const void* q, const void* k, const void* v, long long ld, con
                   const void* dout, long long lddo, const float* lse, float* delta, void* dq, void* dk, void* dv,
                   long long lddqkv, int B, int N, int H, int head_dim, float scale, cudaStream_t stream);
 
+// augment.cu
+int augment_sample_params(long long seed, long long first_sample, int B, int H, int W, int size, int recipe,
+                          int* ints_host, float* floats_host);
+int augment_patchify(const void* images_u8, int B, int H, int W, const int* ints_dev, const float* floats_dev, int size,
+                     const float* mean3_host, const float* std3_host, void* patches_bf16, void* pixels_out_u8,
+                     cudaStream_t stream);
+
 // engine.cu
 struct VitLayout {
   // element offsets into the parameter arena (fp32, bf16 shadow and gradient arenas share the layout)

@@ -62,19 +62,21 @@ class FusedAdamW(torch.optim.Optimizer):
             self._v.copy_(old_v)
         self._arena_ptr = arena.data_ptr()
         trainable = set(id(p) for g in self.param_groups for p in g["params"])
-        ranges = []
+        spans = []
         for p, o, n in zip(model._params_in_order(), model._offsets, model._numels):
             if id(p) not in trainable:
                 continue
-            n_pad = (n + 63) // 64 * 64
-            if ranges and ranges[-1][1] == o:
-                ranges[-1][1] = o + n_pad
-            else:
-                ranges.append([o, o + n_pad])
+            spans.append((o, o + (n + 63) // 64 * 64))
             st = self.state[p]
             st["step"] = torch.tensor(float(self._step))
             st["exp_avg"] = self._m[o:o + n].view(p.shape)
             st["exp_avg_sq"] = self._v[o:o + n].view(p.shape)
+        ranges = []
+        for a, b in sorted(spans):  # arena order differs from named_parameters() order (q/k/v are interleaved)
+            if ranges and ranges[-1][1] == a:
+                ranges[-1][1] = b
+            else:
+                ranges.append([a, b])
         self._ranges = [(a, min(b, arena.numel())) for a, b in ranges]
 
     # ---- torch.optim surface ------------------------------------------------------------------------
