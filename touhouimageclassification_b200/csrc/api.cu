@@ -38,12 +38,12 @@ TIC_API int tic_layernorm_bwd(const void* dy_bf16, int64_t lddy, const float* x,
 
 TIC_API int tic_attention_fwd(const void* q, const void* k, const void* v, int64_t ld, void* o, int64_t ldo, float* lse,
                               int B, int N, int H, int head_dim, float scale, void* stream) {
-  return attention_fwd(q, k, v, ld, o, ldo, lse, B, N, H, head_dim, scale, S(stream));
+  return attention_fwd_tc(q, k, v, ld, o, ldo, lse, B, N, H, head_dim, scale, S(stream));
 }
 TIC_API int tic_attention_bwd(const void* q, const void* k, const void* v, int64_t ld, const void* o, int64_t ldo,
                               const void* dout, int64_t lddo, const float* lse, float* delta_scratch, void* dq, void* dk,
                               void* dv, int64_t lddqkv, int B, int N, int H, int head_dim, float scale, void* stream) {
-  return attention_bwd(q, k, v, ld, o, ldo, dout, lddo, lse, delta_scratch, dq, dk, dv, lddqkv, B, N, H, head_dim, scale,
+  return attention_bwd_tc(q, k, v, ld, o, ldo, dout, lddo, lse, delta_scratch, dq, dk, dv, lddqkv, B, N, H, head_dim, scale,
                        S(stream));
 }
 

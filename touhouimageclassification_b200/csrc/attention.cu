@@ -474,6 +474,15 @@ int attention_fwd(const void* q, const void* k, const void* v, long long ld, voi
   return check_launch("attention_fwd");
 }
 
+int attention_delta(const void* o, long long ldo, const void* dout, long long lddo, float* delta, int B, int N, int H,
+                    cudaStream_t stream) {
+  const long long toks = static_cast<long long>(B) * N;
+  attn_delta_kernel<<<static_cast<int>((toks + 7) / 8), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(o), ldo,
+                                                                          reinterpret_cast<const __nv_bfloat16*>(dout),
+                                                                          lddo, delta, B, N, H);
+  return check_launch("attention_delta");
+}
+
 int attention_bwd(const void* q, const void* k, const void* v, long long ld, const void* o, long long ldo,
                   const void* dout, long long lddo, const float* lse, float* delta, void* dq, void* dk, void* dv,
                   long long lddqkv, int B, int N, int H, int head_dim, float scale, cudaStream_t stream) {

@@ -206,7 +206,7 @@ int vit_forward(const tic_vit_config* c, const float* P32, const void* P16v, con
     TIC_TRY(layernorm_fwd(x_in, D, p32 + L.ln1_w, p32 + L.ln1_b, c->ln_eps, M, D, h1, D, nullptr, 0, mean1, rstd1, st));
     TIC_TRY(gemm_bf16(h1, D, false, p16 + L.qkv_w, D, false, M, 3 * D, D, kEpiBf16, qkv, 3 * D, nullptr, 0,
                       p32 + L.qkv_b, nullptr, 0, 0, 1, st));
-    TIC_TRY(attention_fwd(qkv, qkv + D, qkv + 2 * D, 3 * D, ctx, D, training ? lse : nullptr, B, N, H, 64, scale, st));
+    TIC_TRY(attention_fwd_tc(qkv, qkv + D, qkv + 2 * D, 3 * D, ctx, D, training ? lse : nullptr, B, N, H, 64, scale, st));
     TIC_TRY(gemm_bf16(ctx, D, false, p16 + L.o_w, D, false, M, D, D, kEpiF32Resid, xmid, D, nullptr, 0, p32 + L.o_b,
                       x_in, D, 0, 1, st));
     TIC_TRY(layernorm_fwd(xmid, D, p32 + L.ln2_w, p32 + L.ln2_b, c->ln_eps, M, D, h2, D, nullptr, 0, mean2, rstd2, st));
@@ -306,7 +306,7 @@ int vit_backward(const tic_vit_config* c, const float* P32, const void* P16v, in
                         0, pick_splits(D, D, M), st));
       TIC_TRY(colsum_bf16(dxb, D, M, D, g + L.o_b, st));
       // attention core
-      TIC_TRY(attention_bwd(qkv, qkv + D, qkv + 2 * D, 3 * D, ctx, D, dctx, D, lse, delta, dqkv, dqkv + D, dqkv + 2 * D,
+      TIC_TRY(attention_bwd_tc(qkv, qkv + D, qkv + 2 * D, 3 * D, ctx, D, dctx, D, lse, delta, dqkv, dqkv + D, dqkv + 2 * D,
                             3 * D, B, N, H, 64, scale, st));
       // fused QKV projection
       TIC_TRY(gemm_bf16(dqkv, 3 * D, false, p16 + L.qkv_w, D, true, M, D, 3 * D, kEpiBf16, dh, D, nullptr, 0, nullptr,

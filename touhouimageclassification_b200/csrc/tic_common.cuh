@@ -69,6 +69,13 @@ TIC_DEVINL float gelu_grad_fast(float x) {
   return fmaf(x * 0.39894228040143267794f, e, cdf);
 }
 
+// 2^x on the SFU (MUFU.EX2), flush-to-zero, no range fix-ups: inputs here are <= 0 (softmax exponents).
+TIC_DEVINL float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 TIC_DEVINL float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -285,5 +292,8 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, bool a_mn_m
 // row pitch in elements, box = box0 x box1 elements (box0 * 2 bytes must be <= 128).
 int encode_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t dim0, uint64_t dim1, uint64_t pitch_elems,
                         uint32_t box0, uint32_t box1);
+
+int encode_tmap_3d_bf16(CUtensorMap* out, const void* base, uint64_t dim0, uint64_t dim1, uint64_t dim2,
+                        uint64_t pitch1_elems, uint64_t pitch2_elems, uint32_t box0, uint32_t box1);
 
 }  // namespace tic

@@ -77,6 +77,16 @@ int augment_patchify(const void* images_u8, int B, int H, int W, const int* ints
                      const float* mean3_host, const float* std3_host, void* patches_bf16, void* pixels_out_u8,
                      cudaStream_t stream);
 
+// attention_tc.cu (tcgen05 / TMEM / TMA)
+int attention_fwd_tc(const void* q, const void* k, const void* v, long long ld, void* o, long long ldo, float* lse,
+                     int B, int N, int H, int head_dim, float scale, cudaStream_t stream);
+
+int attention_bwd_tc(const void* q, const void* k, const void* v, long long ld, const void* o, long long ldo,
+                     const void* dout, long long lddo, const float* lse, float* delta, void* dq, void* dk, void* dv,
+                     long long lddqkv, int B, int N, int H, int head_dim, float scale, cudaStream_t stream);
+int attention_delta(const void* o, long long ldo, const void* dout, long long lddo, float* delta, int B, int N, int H,
+                    cudaStream_t stream);
+
 // engine.cu
 struct VitLayout {
   // element offsets into the parameter arena (fp32, bf16 shadow and gradient arenas share the layout)
