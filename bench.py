@@ -166,7 +166,7 @@ def run_reference(args):
                 cpu_baseline=dict(value=value, unit="img/s", cores=cores, kind=kind, sample=sample),
                 e2e=dict(value=value, unit="img/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 gpu_launches=0, roofline=None, clocks=None)
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def base_line(args, n_gpus):
@@ -309,12 +309,31 @@ def run_ours(args):
         if world == 1 and not args.no_cpu_baseline:
             v, ms, kind, cores, sample = cpu_train_steps(steps=2, warmup=1, time_budget_s=60.0)
             line["cpu_baseline"] = dict(value=v, unit="img/s", cores=cores, kind=kind, sample=sample)
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+def protect_stdout():
+    """Libraries (NCCL's version banner) may print to fd 1: keep a private copy for the ONE JSON line and point
+    fd 1 at stderr for everything else."""
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+_JSON_OUT = None
+
+
+def emit(line: dict):
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    protect_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

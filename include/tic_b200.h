@@ -72,17 +72,25 @@ TIC_API int tic_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void
                           const float* bias, const void* aux, int64_t ldaux, int aux_int, int splits, void* stream);
 
 
+/* Same GEMM with the TIC_EPI_BF16_DGELU epilogue that also ACCUMULATES the column sums of its bf16 output into
+ * colsum_accum[N] (the fc1 bias gradient), saving a reduction pass over the [M, 4D] gradient. */
+TIC_API int tic_gemm_bf16_colsum(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major,
+                                 int M, int N, int K, int epilogue, void* out, int64_t ldo, const void* aux, int64_t ldaux,
+                                 float* colsum_accum, void* stream);
+
 /* ---- LayerNorm ---------------------------------------------------------------------------------
  * Replaces nn.LayerNorm (modeling_vit.py:325-326,333,340,455) [a4, a11]. fp32 statistics, eps from
  * ViTConfig.layer_norm_eps. Row pitches are in elements; y_bf16 / y_f32 / mean / rstd may be NULL.
- * Backward: dx = dres + LN'(dy) (dres may alias dx or be NULL); dgamma / dbeta are ACCUMULATED. */
+ * Backward: dx = dres + LN'(dy) (dres may alias dx or be NULL); dgamma / dbeta are ACCUMULATED. dxsum (may be
+ * NULL) ACCUMULATES the column sums of the bf16 dx it writes, i.e. the bias gradient of the Linear layer whose
+ * output gradient that dx is (attention out-proj / fc2), so no separate reduction pass over dx is needed. */
 TIC_API int tic_layernorm_fwd(const float* x, int64_t ldx, const float* gamma, const float* beta, float eps, int rows,
                               int D, void* y_bf16, int64_t ldy, float* y_f32, int64_t ldyf, float* mean, float* rstd,
                               void* stream);
 TIC_API int tic_layernorm_bwd(const void* dy_bf16, int64_t lddy, const float* x, int64_t ldx, const float* mean,
                               const float* rstd, const float* gamma, const float* dres, int64_t lddres, int rows, int D,
                               float* dx, int64_t lddx, void* dx_bf16, int64_t lddxb, float* dgamma, float* dbeta,
-                              void* stream);
+                              float* dxsum, void* stream);
 
 /* ---- fused multi-head attention -----------------------------------------------------------------
  * Replaces F.scaled_dot_product_attention (modeling_vit.py:232-246; sdpa_attention.py:92-103) [a6].

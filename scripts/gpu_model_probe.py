@@ -31,7 +31,7 @@ def t_ln():
         dy = torch.randn(1000, D, device=dev).bfloat16()
         dres = torch.randn(1000, D, device=dev)
         ref.backward(dy.float())
-        dx, dxb, dg, db = ops.layernorm_bwd(dy, x, mean, rstd, g, dres)
+        dx, dxb, dg, db, _ = ops.layernorm_bwd(dy, x, mean, rstd, g, dres)
         print(f"[ln D={D}] fwd f32 {rel(yf, ref):.2e} bf16 {rel(y, ref):.2e} dx {rel(dx - dres, xr.grad):.2e} dgamma {rel(dg, gr.grad):.2e} dbeta {rel(db, br.grad):.2e}", flush=True)
 
 def t_attn():

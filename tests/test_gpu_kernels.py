@@ -76,6 +76,17 @@ def test_gemm_fused_epilogues():
     x = pre2.float().requires_grad_(True)
     F.gelu(x).backward(g)
     assert rel(out, x.grad) < 4e-3
+    # fused bias gradient: column sums of the bf16 output, accumulated
+    cs = torch.zeros(N, device=dev)
+    _lib_out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    from touhouimageclassification_b200 import _lib as L
+    import ctypes
+    L.check(L.load().tic_gemm_bf16_colsum(ctypes.c_void_p(a.data_ptr()), ctypes.c_int64(K), 0, ctypes.c_void_p(bt.data_ptr()),
+                                          ctypes.c_int64(N), 1, M, N, K, ops.EPI_BF16_DGELU, ctypes.c_void_p(_lib_out.data_ptr()),
+                                          ctypes.c_int64(N), ctypes.c_void_p(pre2.data_ptr()), ctypes.c_int64(N),
+                                          ctypes.c_void_p(cs.data_ptr()), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    assert torch.equal(_lib_out, out)
+    assert rel(cs, out.float().sum(0)) < 1e-4
 
 
 def test_gemm_rejects_bad_arguments():
@@ -102,9 +113,10 @@ def test_layernorm_fwd_bwd(D):
     dy = torch.randn(rows, D, device=dev).bfloat16()
     dres = torch.randn(rows, D, device=dev)
     ref.backward(dy.float())
-    dx, dxb, dg, db = ops.layernorm_bwd(dy, x, mean, rstd, g, dres)
+    dx, dxb, dg, db, dxsum = ops.layernorm_bwd(dy, x, mean, rstd, g, dres)
     assert rel(dx - dres, xr.grad) < 1e-5
     assert rel(dxb, dx) < 3e-3
+    assert rel(dxsum, dxb.float().sum(0)) < 1e-5      # fused bias-gradient column sums of the bf16 dx
     assert rel(dg, gr.grad) < 1e-5 and rel(db, br.grad) < 1e-5
 
 

@@ -23,6 +23,13 @@ TIC_API int tic_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void
                    aux, ldaux, aux_int, splits, S(stream));
 }
 
+TIC_API int tic_gemm_bf16_colsum(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major,
+                                 int M, int N, int K, int epilogue, void* out, int64_t ldo, const void* aux, int64_t ldaux,
+                                 float* colsum_accum, void* stream) {
+  return gemm_bf16(A, lda, a_mn_major != 0, B, ldb, b_mn_major != 0, M, N, K, epilogue, out, ldo, nullptr, 0, nullptr, aux,
+                   ldaux, 0, 1, S(stream), colsum_accum);
+}
+
 TIC_API int tic_layernorm_fwd(const float* x, int64_t ldx, const float* gamma, const float* beta, float eps, int rows,
                               int D, void* y_bf16, int64_t ldy, float* y_f32, int64_t ldyf, float* mean, float* rstd,
                               void* stream) {
@@ -31,9 +38,9 @@ TIC_API int tic_layernorm_fwd(const float* x, int64_t ldx, const float* gamma, c
 TIC_API int tic_layernorm_bwd(const void* dy_bf16, int64_t lddy, const float* x, int64_t ldx, const float* mean,
                               const float* rstd, const float* gamma, const float* dres, int64_t lddres, int rows, int D,
                               float* dx, int64_t lddx, void* dx_bf16, int64_t lddxb, float* dgamma, float* dbeta,
-                              void* stream) {
+                              float* dxsum, void* stream) {
   return layernorm_bwd(dy_bf16, lddy, x, ldx, mean, rstd, gamma, dres, lddres, rows, D, dx, lddx, dx_bf16, lddxb,
-                       dgamma, dbeta, S(stream));
+                       dgamma, dbeta, dxsum, S(stream));
 }
 
 TIC_API int tic_attention_fwd(const void* q, const void* k, const void* v, int64_t ld, void* o, int64_t ldo, float* lse,

@@ -262,8 +262,10 @@ int vit_backward(const tic_vit_config* c, const float* P32, const void* P16v, in
       const float* x_last = reinterpret_cast<const float*>(ws + w.x + w.s_x * Lyr);
       const float* fstats = reinterpret_cast<const float*>(ws + w.stats + w.s_stats * 4 * Lyr);
       const long long rs = static_cast<long long>(N) * D;
+      // dx of the last layer's output: its column sums are that layer's fc2 bias gradient
+      float* fc2_b_last = G + L.layer0 + static_cast<long long>(Lyr - 1) * L.layer_stride + L.fc2_b;
       TIC_TRY(layernorm_bwd(ws + w.dhcls, D, x_last, rs, fstats, fstats + B, P32 + L.lnf_w, nullptr, 0, B, D, dx, rs,
-                            dxb, rs, G + L.lnf_w, G + L.lnf_b, st));
+                            dxb, rs, G + L.lnf_w, G + L.lnf_b, fc2_b_last, st));
     } else if (stage <= Lyr) {
       if (head_only) continue;
       const int l = Lyr - stage;
@@ -286,25 +288,22 @@ int vit_backward(const tic_vit_config* c, const float* P32, const void* P16v, in
 
       // fc2: x_out = xmid + act W2^T + b2        (dy = dxb, the bf16 copy of the residual-stream gradient)
       TIC_TRY(gemm_bf16(dxb, D, false, p16 + L.fc2_w, F, true, M, F, D, kEpiBf16DGelu, dact, F, nullptr, 0, nullptr, pre,
-                        F, 0, 1, st));  // dact <- dpre = (dy W2) * gelu'(pre)
+                        F, 0, 1, st, g + L.fc1_b));  // dact <- dpre = (dy W2) * gelu'(pre); fc1 bias grad = colsum(dpre)
       TIC_TRY(gemm_bf16(dxb, D, true, act, F, true, D, F, M, kEpiF32Atomic, g + L.fc2_w, F, nullptr, 0, nullptr, nullptr,
                         0, 0, pick_splits(D, F, M), st));
-      TIC_TRY(colsum_bf16(dxb, D, M, D, g + L.fc2_b, st));
       // fc1: pre = h2 W1^T + b1
       TIC_TRY(gemm_bf16(dact, F, false, p16 + L.fc1_w, D, true, M, D, F, kEpiBf16, dh, D, nullptr, 0, nullptr, nullptr, 0,
                         0, 1, st));
       TIC_TRY(gemm_bf16(dact, F, true, h2, D, true, F, D, M, kEpiF32Atomic, g + L.fc1_w, D, nullptr, 0, nullptr, nullptr,
                         0, 0, pick_splits(F, D, M), st));
-      TIC_TRY(colsum_bf16(dact, F, M, F, g + L.fc1_b, st));
       // layernorm_after + residual
       TIC_TRY(layernorm_bwd(dh, D, xmid, D, mean2, rstd2, p32 + L.ln2_w, dx, D, M, D, dx, D, dxb, D, g + L.ln2_w,
-                            g + L.ln2_b, st));
+                            g + L.ln2_b, g + L.o_b, st));  // + out-proj bias grad = colsum(dxb)
       // attention output projection: xmid = x_in + ctx Wo^T + bo
       TIC_TRY(gemm_bf16(dxb, D, false, p16 + L.o_w, D, true, M, D, D, kEpiBf16, dctx, D, nullptr, 0, nullptr, nullptr, 0,
                         0, 1, st));
       TIC_TRY(gemm_bf16(dxb, D, true, ctx, D, true, D, D, M, kEpiF32Atomic, g + L.o_w, D, nullptr, 0, nullptr, nullptr, 0,
                         0, pick_splits(D, D, M), st));
-      TIC_TRY(colsum_bf16(dxb, D, M, D, g + L.o_b, st));
       // attention core
       TIC_TRY(attention_bwd_tc(qkv, qkv + D, qkv + 2 * D, 3 * D, ctx, D, dctx, D, lse, delta, dqkv, dqkv + D, dqkv + 2 * D,
                             3 * D, B, N, H, 64, scale, st));
@@ -315,8 +314,9 @@ int vit_backward(const tic_vit_config* c, const float* P32, const void* P16v, in
                         nullptr, 0, 0, pick_splits(3 * D, D, M), st));
       TIC_TRY(colsum_bf16(dqkv, 3 * D, M, 3 * D, g + L.qkv_b, st));
       // layernorm_before + residual
+      // dx of layer l's input == gradient of layer (l-1)'s output: its column sums are that layer's fc2 bias gradient
       TIC_TRY(layernorm_bwd(dh, D, x_in, D, mean1, rstd1, p32 + L.ln1_w, dx, D, M, D, dx, D, l > 0 ? dxb : nullptr, D,
-                            g + L.ln1_w, g + L.ln1_b, st));
+                            g + L.ln1_w, g + L.ln1_b, l > 0 ? g - L.layer_stride + L.fc2_b : nullptr, st));
     } else {
       if (head_only) continue;
       TIC_TRY(embed_bwd(dx, B, N, D, G + L.pos, G + L.cls, ws + w.dpatch, st));

@@ -51,6 +51,7 @@ struct GemmParams {
   const void* aux;
   long long ldaux;
   int aux_int;  // kEpiF32PosEmbed: patches per image (P)
+  float* colsum;  // kEpiBf16DGelu: optional, accumulates column sums of the bf16 output (bias gradient)
 };
 
 template <bool A_MN, bool B_MN, int EPI>
@@ -239,6 +240,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         __syncwarp();
         if (col < p.N) {
           float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
+          float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
           if constexpr (EPI != kEpiF32Atomic && EPI != kEpiBf16DGelu) {
             if (p.bias != nullptr) bias = __ldg(reinterpret_cast<const float4*>(p.bias + col));
           }
@@ -264,9 +266,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             } else if constexpr (EPI == kEpiBf16DGelu) {
               const uint2 pre = auxh[i];
               const float g0 = round_bf16(a.x), g1 = round_bf16(a.y), g2 = round_bf16(a.z), g3 = round_bf16(a.w);
-              *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<long long>(row) * p.ldo + col) =
-                  make_uint2(pack_bf16x2(g0 * gelu_grad_fast(bf16_lo(pre.x)), g1 * gelu_grad_fast(bf16_hi(pre.x))),
-                             pack_bf16x2(g2 * gelu_grad_fast(bf16_lo(pre.y)), g3 * gelu_grad_fast(bf16_hi(pre.y))));
+              const uint2 w = make_uint2(pack_bf16x2(g0 * gelu_grad_fast(bf16_lo(pre.x)), g1 * gelu_grad_fast(bf16_hi(pre.x))),
+                                         pack_bf16x2(g2 * gelu_grad_fast(bf16_lo(pre.y)), g3 * gelu_grad_fast(bf16_hi(pre.y))));
+              *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<long long>(row) * p.ldo + col) = w;
+              csum.x += bf16_lo(w.x); csum.y += bf16_hi(w.x); csum.z += bf16_lo(w.y); csum.w += bf16_hi(w.y);
             } else if constexpr (EPI == kEpiF32Resid) {
               // bf16 GEMM output added to the fp32 residual stream (Appendix B).
               const float4 x = auxf[i];
@@ -285,6 +288,21 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
               *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) +
                                          (static_cast<long long>(img) * (P + 1) + 1 + pidx) * p.ldo + col) =
                   make_float4(round_bf16(a.x) + x.x, round_bf16(a.y) + x.y, round_bf16(a.z) + x.z, round_bf16(a.w) + x.w);
+            }
+          }
+          if constexpr (EPI == kEpiBf16DGelu) {
+            if (p.colsum != nullptr) {  // lanes with the same 4-column group (lane & 7) hold partial sums over 8 rows each
+#pragma unroll
+              for (int o = 8; o < 32; o <<= 1) {
+                csum.x += __shfl_xor_sync(0xffffffffu, csum.x, o);
+                csum.y += __shfl_xor_sync(0xffffffffu, csum.y, o);
+                csum.z += __shfl_xor_sync(0xffffffffu, csum.z, o);
+                csum.w += __shfl_xor_sync(0xffffffffu, csum.w, o);
+              }
+              if (lane < 8) {
+                atomicAdd(p.colsum + col + 0, csum.x); atomicAdd(p.colsum + col + 1, csum.y);
+                atomicAdd(p.colsum + col + 2, csum.z); atomicAdd(p.colsum + col + 3, csum.w);
+              }
             }
           }
         }
@@ -338,7 +356,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cu
 // B: K-major => [N, K] row-major with pitch ldb; MN-major => [K, N] row-major with pitch ldb.
 int gemm_bf16(const void* A, long long lda, bool a_mn, const void* B, long long ldb, bool b_mn, int M, int N, int K,
               int epilogue, void* out, long long ldo, void* out2, long long ldo2, const float* bias, const void* aux,
-              long long ldaux, int aux_int, int splits, cudaStream_t stream) {
+              long long ldaux, int aux_int, int splits, cudaStream_t stream, float* colsum) {
   if (M <= 0 || N <= 0 || K <= 0) return set_error(kErrInvalidArg, "gemm: empty problem %dx%dx%d", M, N, K);
   if (N % 8 != 0) return set_error(kErrInvalidArg, "gemm: N=%d must be a multiple of 8", N);
   if ((lda % 8) || (ldb % 8)) return set_error(kErrInvalidArg, "gemm: operand pitches must be multiples of 8 elements");
@@ -367,7 +385,7 @@ int gemm_bf16(const void* A, long long lda, bool a_mn, const void* B, long long 
   GemmParams p;
   p.M = M; p.N = N; p.K = K; p.splits = splits;
   p.out = out; p.ldo = ldo; p.out2 = out2; p.ldo2 = ldo2;
-  p.bias = bias; p.aux = aux; p.ldaux = ldaux; p.aux_int = aux_int;
+  p.bias = bias; p.aux = aux; p.ldaux = ldaux; p.aux_int = aux_int; p.colsum = colsum;
 
   static const char* kNames[2][2][7] = {
       {{"gemm_fwd_bf16", "gemm_fwd_gelu", "gemm_fwd_resid", "gemm_fwd_x", "gemm_fwd_f32", "gemm_fwd_x", "gemm_fwd_posemb"},

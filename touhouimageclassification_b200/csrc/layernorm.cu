@@ -72,18 +72,21 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long lddy, const float*
               const float* __restrict__ mean_in, const float* __restrict__ rstd_in, const float* __restrict__ gamma,
               const float* dres, long long lddres, int rows, float* dx, long long lddx,
               __nv_bfloat16* __restrict__ dx_bf16, long long lddxb, float* __restrict__ dgamma,
-              float* __restrict__ dbeta) {
+              float* __restrict__ dbeta, float* __restrict__ dxsum) {
   constexpr int D = VEC * 128;
   extern __shared__ float4 ln_smem[];
   float4* sg = ln_smem;                           // [LN_WARPS][VEC * 32] dgamma partials
   float4* sb = ln_smem + LN_WARPS * VEC * 32;     // [LN_WARPS][VEC * 32] dbeta partials
+  float4* sc = ln_smem + 2 * LN_WARPS * VEC * 32; // [LN_WARPS][VEC * 32] column sums of the emitted bf16 dx
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float4* my_g = sg + warp * VEC * 32;
   float4* my_b = sb + warp * VEC * 32;
+  float4* my_c = sc + warp * VEC * 32;
 #pragma unroll
   for (int i = 0; i < VEC; ++i) {
     my_g[lane + 32 * i] = make_float4(0.f, 0.f, 0.f, 0.f);
     my_b[lane + 32 * i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    my_c[lane + 32 * i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   const float4* g4 = reinterpret_cast<const float4*>(gamma);
   for (int row = blockIdx.x * LN_WARPS + warp; row < rows; row += gridDim.x * LN_WARPS) {
@@ -127,17 +130,27 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long lddy, const float*
         w.x = pack_bf16x2(o.x, o.y);
         w.y = pack_bf16x2(o.z, o.w);
         reinterpret_cast<uint2*>(dx_bf16 + static_cast<long long>(row) * lddxb)[lane + 32 * i] = w;
+        if (dxsum != nullptr) {  // bias gradient of the Linear whose output gradient this dx is (sum of the bf16 values)
+          float4 ac = my_c[lane + 32 * i];
+          ac.x += bf16_lo(w.x); ac.y += bf16_hi(w.x); ac.z += bf16_lo(w.y); ac.w += bf16_hi(w.y);
+          my_c[lane + 32 * i] = ac;
+        }
       }
     }
   }
   __syncthreads();
   for (int c = threadIdx.x; c < VEC * 32; c += LN_WARPS * 32) {
-    float4 s = sg[c], t = sb[c];
+    float4 s = sg[c], t = sb[c], u = sc[c];
 #pragma unroll
     for (int w = 1; w < LN_WARPS; ++w) {
-      const float4 a = sg[w * VEC * 32 + c], b = sb[w * VEC * 32 + c];
+      const float4 a = sg[w * VEC * 32 + c], b = sb[w * VEC * 32 + c], e = sc[w * VEC * 32 + c];
       s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
       t.x += b.x; t.y += b.y; t.z += b.z; t.w += b.w;
+      u.x += e.x; u.y += e.y; u.z += e.z; u.w += e.w;
+    }
+    if (dxsum != nullptr) {
+      atomicAdd(dxsum + 4 * c + 0, u.x); atomicAdd(dxsum + 4 * c + 1, u.y);
+      atomicAdd(dxsum + 4 * c + 2, u.z); atomicAdd(dxsum + 4 * c + 3, u.w);
     }
     if (dgamma != nullptr) {
       atomicAdd(dgamma + 4 * c + 0, s.x); atomicAdd(dgamma + 4 * c + 1, s.y);
@@ -178,25 +191,27 @@ int layernorm_fwd(const float* x, long long ldx, const float* gamma, const float
 int layernorm_bwd(const void* dy_bf16, long long lddy, const float* x, long long ldx, const float* mean,
                   const float* rstd, const float* gamma, const float* dres, long long lddres, int rows, int D,
                   float* dx, long long lddx, void* dx_bf16, long long lddxb, float* dgamma, float* dbeta,
-                  cudaStream_t stream) {
+                  float* dxsum, cudaStream_t stream) {
   if (rows <= 0) return kOk;
   if (D % 128 != 0) return set_error(kErrUnsupported, "layernorm: D=%d must be a multiple of 128", D);
+  if (dxsum != nullptr && dx_bf16 == nullptr)
+    return set_error(kErrInvalidArg, "layernorm_bwd: dxsum needs the bf16 dx output");
   int grid = (rows + LN_WARPS - 1) / LN_WARPS;
-  const int max_grid = 148 * 3;
+  const int max_grid = 148 * 2;
   if (grid > max_grid) grid = max_grid;
   ProfScope prof("layernorm_bwd", 0.0, static_cast<double>(rows) * D * (2 + 4 + (dres ? 4 : 0) + 4 + (dx_bf16 ? 2 : 0)), stream);
   auto* dyb = reinterpret_cast<const __nv_bfloat16*>(dy_bf16);
   auto* dxb = reinterpret_cast<__nv_bfloat16*>(dx_bf16);
 #define TIC_LN_BWD(V)                                                                                             \
   case V: {                                                                                                       \
-    const int smem = 2 * LN_WARPS * V * 32 * 16;                                                                  \
+    const int smem = 3 * LN_WARPS * V * 32 * 16;                                                                  \
     static bool attr_set = false;                                                                                 \
     if (!attr_set && smem > 48 * 1024) {                                                                          \
       cudaFuncSetAttribute(ln_bwd_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);                  \
       attr_set = true;                                                                                            \
     }                                                                                                             \
     ln_bwd_kernel<V><<<grid, LN_WARPS * 32, smem, stream>>>(dyb, lddy, x, ldx, mean, rstd, gamma, dres, lddres, rows, \
-                                                            dx, lddx, dxb, lddxb, dgamma, dbeta);                 \
+                                                            dx, lddx, dxb, lddxb, dgamma, dbeta, dxsum);          \
     break;                                                                                                        \
   }
   switch (D / 128) {

@@ -32,7 +32,7 @@ enum Epilogue : int {
 // gemm_tcgen05.cu
 int gemm_bf16(const void* A, long long lda, bool a_mn, const void* B, long long ldb, bool b_mn, int M, int N, int K,
               int epilogue, void* out, long long ldo, void* out2, long long ldo2, const float* bias, const void* aux,
-              long long ldaux, int aux_int, int splits, cudaStream_t stream);
+              long long ldaux, int aux_int, int splits, cudaStream_t stream, float* colsum = nullptr);
 
 // layernorm.cu
 int layernorm_fwd(const float* x, long long ldx, const float* gamma, const float* beta, float eps, int rows, int D,
@@ -41,7 +41,7 @@ int layernorm_fwd(const float* x, long long ldx, const float* gamma, const float
 int layernorm_bwd(const void* dy_bf16, long long lddy, const float* x, long long ldx, const float* mean,
                   const float* rstd, const float* gamma, const float* dres, long long lddres, int rows, int D,
                   float* dx, long long lddx, void* dx_bf16, long long lddxb, float* dgamma, float* dbeta,
-                  cudaStream_t stream);
+                  float* dxsum, cudaStream_t stream);
 
 // elementwise.cu
 int patchify_f32(const float* x, void* out_bf16, int B, int S, cudaStream_t stream);

@@ -80,11 +80,12 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, dres=None):
     dxb = torch.empty((rows, D), device=x.device, dtype=torch.bfloat16)
     dgamma = torch.zeros(D, device=x.device, dtype=torch.float32)
     dbeta = torch.zeros(D, device=x.device, dtype=torch.float32)
+    dxsum = torch.zeros(D, device=x.device, dtype=torch.float32)
     _lib.check(_lib.load().tic_layernorm_bwd(_p(dy), c_i64(dy.stride(0)), _p(x), c_i64(x.stride(0)), _p(mean), _p(rstd),
                                              _p(gamma), _p(dres), c_i64(0 if dres is None else dres.stride(0)),
                                              c_int(rows), c_int(D), _p(dx), c_i64(D), _p(dxb), c_i64(D), _p(dgamma),
-                                             _p(dbeta), _s()))
-    return dx, dxb, dgamma, dbeta
+                                             _p(dbeta), _p(dxsum), _s()))
+    return dx, dxb, dgamma, dbeta, dxsum
 
 
 def attention_fwd(qkv, B, N, H, scale=0.125, need_lse=True):
