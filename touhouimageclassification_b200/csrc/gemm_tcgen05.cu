@@ -24,20 +24,29 @@ namespace tic {
 
 namespace {
 
-constexpr int BM = 128;
+constexpr int BM = 128;   // accumulator rows per CTA (one TMEM lane per row)
 constexpr int BN = 256;
 constexpr int BK = 64;
 constexpr int UMMA_K = 16;
-constexpr int STAGES = 4;
 constexpr int ACC_STAGES = 2;
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
-constexpr int B_STAGE_BYTES = BN * BK * 2;  // 32 KB
-constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_THREADS = (NUM_EPI_WARPS + 2) * 32;
 constexpr int TMEM_COLS = ACC_STAGES * BN;  // 512
 constexpr int EPI_STAGE_BYTES = 32 * 32 * 4;  // per epilogue warp: 32 rows x 32 fp32 columns
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + NUM_EPI_WARPS * EPI_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+
+// NCTA = 1: one CTA computes a 128 x 256 tile.  NCTA = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) computes a
+// 256 x 256 tile with one UMMA M=256: each CTA stages its own 128 A rows and HALF of the B tile (128 of the 256
+// N rows), which halves the L2 -> smem operand traffic per FLOP and frees smem for a deeper ring.
+template <int NCTA>
+struct Cfg {
+  static constexpr int B_ROWS = BN / NCTA;                 // B rows (N) staged per CTA
+  static constexpr int B_STAGE_BYTES = B_ROWS * BK * 2;    // 32 KB / 16 KB
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int STAGES = NCTA == 2 ? 6 : 4;
+  static constexpr int TILE_M = BM * NCTA;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + NUM_EPI_WARPS * EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
 
 
 struct GemmParams {
@@ -54,10 +63,17 @@ struct GemmParams {
   float* colsum;  // kEpiBf16DGelu: optional, accumulates column sums of the bf16 output (bias gradient)
 };
 
-template <bool A_MN, bool B_MN, int EPI>
+template <bool A_MN, bool B_MN, int EPI, int NCTA>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const GemmParams p) {
+  using C = Cfg<NCTA>;
+  constexpr int STAGES = C::STAGES;
+  constexpr int B_STAGE_BYTES = C::B_STAGE_BYTES;
+  constexpr int STAGE_BYTES = C::STAGE_BYTES;
+  const uint32_t cta_rank = NCTA == 2 ? cluster_ctarank() : 0u;   // 0 = leader of the pair
+  const int worker = NCTA == 2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int num_workers = NCTA == 2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B atoms are 1024 B: align the operand ring.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -74,7 +90,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  const int m_blocks = (p.M + BM - 1) / BM;
+  const int m_blocks = (p.M + C::TILE_M - 1) / C::TILE_M;
   const int n_blocks = (p.N + BN - 1) / BN;
   const int k_blocks_total = (p.K + BK - 1) / BK;
   const int k_blocks_per_split = (k_blocks_total + p.splits - 1) / p.splits;
@@ -85,23 +101,26 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
   }
+  if constexpr (NCTA == 2) cluster_sync_all();  // both CTAs are resident before the paired TMEM allocation
   if (warp == 9) {
     if (lane == 0) {
       for (int i = 0; i < STAGES; ++i) {
-        mbar_init(&full_bar[i], 1);
+        mbar_init(&full_bar[i], NCTA);   // the leader's barrier collects one producer arrival per CTA
         mbar_init(&empty_bar[i], 1);
       }
       for (int i = 0; i < ACC_STAGES; ++i) {
         mbar_init(&tmem_full_bar[i], 1);
-        mbar_init(&tmem_empty_bar[i], NUM_EPI_WARPS);
+        mbar_init(&tmem_empty_bar[i], NUM_EPI_WARPS * NCTA);
       }
       fence_mbar_init();
     }
     __syncwarp();
-    tmem_alloc(tmem_base_slot, TMEM_COLS);
+    if constexpr (NCTA == 2) tmem_alloc_2cta(tmem_base_slot, TMEM_COLS);
+    else tmem_alloc(tmem_base_slot, TMEM_COLS);
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (NCTA == 2) cluster_sync_all();
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
 
@@ -110,32 +129,37 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      auto load = [&](void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+        if constexpr (NCTA == 2) tma_load_2d_2cta(dst, map, bar, c0, c1);
+        else tma_load_2d(dst, map, bar, c0, c1);
+      };
+      for (int tile = worker; tile < total_tiles; tile += num_workers) {
         const int split = tile / tiles_per_split;
         const int rem = tile - split * tiles_per_split;
-        const int m_idx = (rem / n_blocks) * BM;
-        const int n_idx = (rem % n_blocks) * BN;
+        const int m_idx = (rem / n_blocks) * C::TILE_M + static_cast<int>(cta_rank) * BM;        // this CTA's A rows
+        const int n_idx = (rem % n_blocks) * BN + static_cast<int>(cta_rank) * C::B_ROWS;        // this CTA's B rows
         const int kb_begin = split * k_blocks_per_split;
         const int kb_end = min(k_blocks_total, kb_begin + k_blocks_per_split);
         for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+          if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES * NCTA);
+          else mbar_arrive_cluster(&full_bar[stage], 0);
           uint8_t* sa = smem_a + stage * A_STAGE_BYTES;
           uint8_t* sb = smem_b + stage * B_STAGE_BYTES;
           const int k_idx = kb * BK;
           if constexpr (!A_MN) {
-            tma_load_2d(sa, &tmap_a, &full_bar[stage], k_idx, m_idx);  // box {64 k, 128 rows}
+            load(sa, &tmap_a, &full_bar[stage], k_idx, m_idx);  // box {64 k, 128 rows}
           } else {
 #pragma unroll
             for (int j = 0; j < BM / 64; ++j)  // boxes {64 m, 64 k}
-              tma_load_2d(sa + j * (64 * BK * 2), &tmap_a, &full_bar[stage], m_idx + 64 * j, k_idx);
+              load(sa + j * (64 * BK * 2), &tmap_a, &full_bar[stage], m_idx + 64 * j, k_idx);
           }
           if constexpr (!B_MN) {
-            tma_load_2d(sb, &tmap_b, &full_bar[stage], k_idx, n_idx);  // box {64 k, 256 rows}
+            load(sb, &tmap_b, &full_bar[stage], k_idx, n_idx);  // box {64 k, B_ROWS rows}
           } else {
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j)  // boxes {64 n, 64 k}
-              tma_load_2d(sb + j * (64 * BK * 2), &tmap_b, &full_bar[stage], n_idx + 64 * j, k_idx);
+            for (int j = 0; j < C::B_ROWS / 64; ++j)  // boxes {64 n, 64 k}
+              load(sb + j * (64 * BK * 2), &tmap_b, &full_bar[stage], n_idx + 64 * j, k_idx);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -143,8 +167,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     }
   } else if (warp == 9) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN, B_MN);
+    if (lane == 0 && cta_rank == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(C::TILE_M, BN, A_MN, B_MN);
       // K-major SW128: 8-row atoms 1024 B apart (SBO); LBO unused.
       // MN-major SW128: atoms of 64 (MN) x 8 (K); next 8 k-rows at SBO = 1024 B, next 64-wide MN chunk at
       // LBO = 64 * BK * 2 = 8192 B (one TMA box).
@@ -155,7 +179,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       uint32_t phase = 0;
       int acc_stage = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = worker; tile < total_tiles; tile += num_workers) {
         const int split = tile / tiles_per_split;
         const int kb_begin = split * k_blocks_per_split;
         const int kb_end = min(k_blocks_total, kb_begin + k_blocks_per_split);
@@ -169,12 +193,18 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           const uint64_t b_desc = make_smem_desc_sw128(smem_u32(smem_b + stage * B_STAGE_BYTES), b_lbo, 1024);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
-            umma_bf16_ss(tmem_d, a_desc + k * a_kstep, b_desc + k * b_kstep, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+            const uint32_t acc = (kb > kb_begin || k > 0) ? 1u : 0u;
+            if constexpr (NCTA == 2) umma_bf16_ss_2cta(tmem_d, a_desc + k * a_kstep, b_desc + k * b_kstep, idesc, acc);
+            else umma_bf16_ss(tmem_d, a_desc + k * a_kstep, b_desc + k * b_kstep, idesc, acc);
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+          // frees the smem slot (in both CTAs of a pair) once these MMAs have read it
+          if constexpr (NCTA == 2) umma_commit_2cta(&empty_bar[stage], 3);
+          else umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full_bar[acc_stage]);  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue warps (of both CTAs)
+        if constexpr (NCTA == 2) umma_commit_2cta(&tmem_full_bar[acc_stage], 3);
+        else umma_commit(&tmem_full_bar[acc_stage]);
         if (++acc_stage == ACC_STAGES) { acc_stage = 0; acc_phase ^= 1; }
       }
     }
@@ -192,10 +222,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     const int ch = lane & 7;        // phase B: 16-byte chunk (4 fp32 columns)
     int acc_stage = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = worker; tile < total_tiles; tile += num_workers) {
       const int split = tile / tiles_per_split;
       const int rem = tile - split * tiles_per_split;
-      const int m_idx = (rem / n_blocks) * BM;
+      const int m_idx = (rem / n_blocks) * C::TILE_M + static_cast<int>(cta_rank) * BM;  // this CTA's accumulator rows
       const int n_idx = (rem % n_blocks) * BN;
       mbar_wait(&tmem_full_bar[acc_stage], acc_phase);
       tc_fence_after();
@@ -311,15 +341,22 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       // All TMEM reads of this warp have completed (wait::ld above): hand the accumulator stage back.
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc_stage]);
+      if (lane == 0) {
+        if constexpr (NCTA == 2) mbar_arrive_cluster(&tmem_empty_bar[acc_stage], 0);  // the leader owns the MMA pipeline
+        else mbar_arrive(&tmem_empty_bar[acc_stage]);
+      }
       if (++acc_stage == ACC_STAGES) { acc_stage = 0; acc_phase ^= 1; }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (NCTA == 2) cluster_sync_all();  // remote arrivals and the peer's smem reads have all landed
+  else __syncthreads();
   tc_fence_after();
-  if (warp == 9) tmem_dealloc(tmem_base, TMEM_COLS);
+  if (warp == 9) {
+    if constexpr (NCTA == 2) tmem_dealloc_2cta(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
+  }
 }
 
 int g_num_sms = 0;
@@ -334,19 +371,36 @@ int num_sms() {
   return g_num_sms;
 }
 
+constexpr int kNcta = 2;  // CTA pairs (tcgen05 cta_group::2)
+
 template <bool A_MN, bool B_MN, int EPI>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
-  auto kern = gemm_bf16_tcgen05_kernel<A_MN, B_MN, EPI>;
+  using C = Cfg<kNcta>;
+  auto kern = gemm_bf16_tcgen05_kernel<A_MN, B_MN, EPI, kNcta>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) return set_error(kErrCuda, "gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  const int m_blocks = (p.M + BM - 1) / BM, n_blocks = (p.N + BN - 1) / BN;
+  const int m_blocks = (p.M + C::TILE_M - 1) / C::TILE_M, n_blocks = (p.N + BN - 1) / BN;
   const int total = m_blocks * n_blocks * p.splits;
-  const int grid = total < num_sms() ? total : num_sms();
-  kern<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, p);
+  const int max_workers = num_sms() / kNcta;
+  const int workers = total < max_workers ? total : max_workers;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(workers * kNcta);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kNcta;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, p);
+  if (e != cudaSuccess) return set_error(kErrCuda, "gemm: cudaLaunchKernelEx: %s", cudaGetErrorString(e));
   return check_launch("gemm_bf16_tcgen05");
 }
 
@@ -378,7 +432,7 @@ int gemm_bf16(const void* A, long long lda, bool a_mn, const void* B, long long 
   if (!a_mn) rc = encode_tmap_2d_bf16(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, 64, BM);
   else       rc = encode_tmap_2d_bf16(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 64, BK);
   if (rc) return rc;
-  if (!b_mn) rc = encode_tmap_2d_bf16(&tb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, 64, BN);
+  if (!b_mn) rc = encode_tmap_2d_bf16(&tb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, 64, Cfg<kNcta>::B_ROWS);
   else       rc = encode_tmap_2d_bf16(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, BK);
   if (rc) return rc;
 

@@ -262,6 +262,66 @@ TIC_DEVINL void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t (&r)[16]) {
 }
 
 // ----------------------------------------------------------------------------------------------
+// CTA pairs (cta_group::2): two SMs of one cluster execute one 256-row UMMA; only the leader (cluster rank 0)
+// issues tcgen05.mma / tcgen05.commit, both CTAs load their own operand halves and own 128 accumulator rows.
+// ----------------------------------------------------------------------------------------------
+TIC_DEVINL uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+TIC_DEVINL void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `bar` in the LEADER CTA of a pair (clears the peer bit, as CUTLASS' Sm100MmaPeerBitMask).
+TIC_DEVINL uint32_t leader_smem_u32(const void* p) { return smem_u32(p) & 0xFEFFFFFFu; }
+// arrive on the same-offset mbarrier of CTA `cta` of this cluster
+TIC_DEVINL void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 remote;\n\t"
+      "mapa.shared::cluster.u32 remote, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [remote];\n\t"
+      "}\n" ::"r"(smem_u32(bar)), "r"(cta)
+      : "memory");
+}
+TIC_DEVINL void tma_load_2d_2cta(void* smem_dst, const void* desc, uint64_t* bar, int32_t c0, int32_t c1) {
+  // executed by both CTAs of the pair; the transaction bytes are credited to the leader's barrier
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      :
+      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(desc)), "r"(leader_smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+TIC_DEVINL void tmem_alloc_2cta(uint32_t* smem_out, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_out)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+TIC_DEVINL void tmem_dealloc_2cta(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+TIC_DEVINL void umma_bf16_ss_2cta(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n"
+      :
+      : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// commit -> arrive on the same-offset mbarrier in every CTA of `mask`
+TIC_DEVINL void umma_commit_2cta(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+
+// ----------------------------------------------------------------------------------------------
 // UMMA descriptors (bit layout follows the PTX ISA "matrix descriptor" / "instruction descriptor").
 // ----------------------------------------------------------------------------------------------
 // Shared-memory matrix descriptor, SWIZZLE_128B, sm_100 version field = 1.
