@@ -65,7 +65,8 @@ enum {
   TIC_EPI_BF16_DGELU = 3,
   TIC_EPI_F32 = 4,
   TIC_EPI_F32_ATOMIC = 5,
-  TIC_EPI_F32_POSEMB = 6
+  TIC_EPI_F32_POSEMB = 6,
+  TIC_EPI_F32_GELU = 7 /* out(f32) = gelu_erf(acc + bias), exact erff (fp32 mode) */
 };
 TIC_API int tic_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major,
                           int M, int N, int K, int epilogue, void* out, int64_t ldo, void* out2, int64_t ldo2,
@@ -187,6 +188,23 @@ TIC_API int tic_vit_forward(const tic_vit_config* cfg, const float* params_f32, 
 TIC_API int tic_vit_backward(const tic_vit_config* cfg, const float* params_f32, const void* params_bf16, int batch,
                              void* workspace, int64_t workspace_bytes, const float* dlogits, float* grads_f32,
                              int stage_begin, int stage_end, int head_only, void* stream);
+
+/* ---- fp32-accurate inference ("fp32 mode") ------------------------------------------------------------
+ * The reference serves with no autocast, i.e. in plain fp32 (TIC/utils/serve.py:99-101 [a21], web/runtime.py:115-116
+ * [a22]). Tensor cores have no fp32 operand type, so every Linear runs as a split-bf16 GEMM on the same tcgen05
+ * kernel: x = hi + mid + lo (three bf16 terms = 24 mantissa bits), likewise w, and the six cross terms larger than
+ * 2^-24 are one GEMM over a 6x longer reduction dimension with fp32 accumulation in tensor memory. LayerNorm, exact-erf
+ * GELU, residual adds, softmax and the attention products are fp32 on the CUDA cores. Forward only.
+ *   tic_vit_w6_elems            bf16 elements of the split weight buffer (6x the GEMM weights)
+ *   tic_vit_prepare_w6          split the GEMM weights of the fp32 arena into it (once per weight update)
+ *   tic_vit_workspace_bytes_f32 workspace for a batch
+ *   tic_vit_forward_f32         pixels fp32 [B,3,S,S] -> logits fp32 [B, num_labels] */
+TIC_API int64_t tic_vit_w6_elems(const tic_vit_config* cfg);
+TIC_API int64_t tic_vit_workspace_bytes_f32(const tic_vit_config* cfg, int batch);
+TIC_API int tic_vit_prepare_w6(const tic_vit_config* cfg, const float* params_f32, void* w6_bf16, void* stream);
+TIC_API int tic_vit_forward_f32(const tic_vit_config* cfg, const float* params_f32, const void* w6_bf16,
+                                const float* pixels, int batch, void* workspace, int64_t workspace_bytes, float* logits,
+                                void* stream);
 
 #ifdef __cplusplus
 }

@@ -60,11 +60,15 @@ def sample_params(seed: int, sample: int, height: int, width: int, size: int = O
     floats = [brightness, contrast, saturation, hue]
     """
     st = Stream(seed, sample)
+    do_crop = do_flip = do_erase = recipe in ("full", "generalization")
+    do_jitter = recipe in ("full", "diversity")
+    do_gray = recipe in ("full", "diversity", "grey")
+    assert recipe in ("full", "generalization", "diversity", "grey", "none")
     area = height * width
     lr0, lr1 = math.log(3.0 / 4.0), math.log(4.0 / 3.0)
     top = left = 0
     h, w = height, width
-    for _ in range(10):  # v2/_geometry.py:277-292
+    for _ in range(10 if do_crop else 0):  # v2/_geometry.py:277-292
         target_area = area * st.uniform(0.08, 1.0)
         aspect = math.exp(st.uniform(lr0, lr1))
         cw = int(round(math.sqrt(target_area * aspect)))
@@ -74,9 +78,11 @@ def sample_params(seed: int, sample: int, height: int, width: int, size: int = O
             left = st.randint(width - cw + 1)
             h, w = chh, cw
             break
-    else:  # central-crop fallback (:293-306)
+    else:  # central-crop fallback (:293-306); Resize-only recipes keep the whole frame
         in_ratio = float(width) / float(height)
-        if in_ratio < 3.0 / 4.0:
+        if not do_crop:
+            pass
+        elif in_ratio < 3.0 / 4.0:
             w = width
             h = int(round(w / (3.0 / 4.0)))
         elif in_ratio > 4.0 / 3.0:
@@ -85,18 +91,21 @@ def sample_params(seed: int, sample: int, height: int, width: int, size: int = O
         else:
             w, h = width, height
         top, left = (height - h) // 2, (width - w) // 2
-    flip = 1 if st.uniform() < 0.5 else 0                      # _transform.py:181
+    flip = (1 if st.uniform() < 0.5 else 0) if do_flip else 0  # _transform.py:181
     perm = [0, 1, 2, 3]                                         # randperm(4): Fisher-Yates on the hash stream
-    for i in range(3, 0, -1):
-        j = st.randint(i + 1)
-        perm[i], perm[j] = perm[j], perm[i]
-    b = st.uniform(0.8, 1.2)
-    c = st.uniform(0.8, 1.2)
-    s = st.uniform(0.8, 1.2)
-    hue = st.uniform(-0.1, 0.1)
-    gray = 1 if st.uniform() < 0.2 else 0
+    b = c = s = 1.0
+    hue = 0.0
+    if do_jitter:
+        for i in range(3, 0, -1):
+            j = st.randint(i + 1)
+            perm[i], perm[j] = perm[j], perm[i]
+        b = st.uniform(0.8, 1.2)
+        c = st.uniform(0.8, 1.2)
+        s = st.uniform(0.8, 1.2)
+        hue = st.uniform(-0.1, 0.1)
+    gray = (1 if st.uniform() < 0.2 else 0) if do_gray else 0
     ei = ej = eh = ew = 0
-    if st.uniform() < 0.5:                                      # RandomErasing gate
+    if do_erase and st.uniform() < 0.5:                         # RandomErasing gate
         el0, el1 = math.log(0.3), math.log(3.3)
         for _ in range(10):                                     # v2/_augment.py:113-131
             erase_area = size * size * st.uniform(0.02, 0.33)
@@ -109,9 +118,7 @@ def sample_params(seed: int, sample: int, height: int, width: int, size: int = O
             ej = st.randint(size - ww + 1)
             eh, ew = hh, ww
             break
-    jitter_on = 1
-    if recipe == "generalization":   # ntrain.py:127-134: crop + flip + erase only
-        jitter_on, gray = 0, 0
+    jitter_on = 1 if do_jitter else 0
     ints = [top, left, h, w, flip, perm[0], perm[1], perm[2], perm[3], gray, ei, ej, eh, ew, jitter_on, 0]
     floats = [b, c, s, hue]
     return np.array(ints, dtype=np.int32), np.array(floats, dtype=np.float32)

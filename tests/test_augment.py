@@ -19,7 +19,8 @@ def smooth_images(B, H, W, seed):
 # ---------------------------------------------------------------------------------------------- CPU (no GPU needed)
 def test_native_sampler_matches_oracle_sampler(lib):
     from touhouimageclassification_b200.augment import sample_params
-    for (seed, first, H, W, recipe) in ((7, 100, 256, 256, "full"), (1, 0, 300, 200, "full"), (5, 12345, 64, 640, "generalization")):
+    for (seed, first, H, W, recipe) in ((7, 100, 256, 256, "full"), (1, 0, 300, 200, "full"), (5, 12345, 64, 640, "generalization"),
+                                        (2, 5, 256, 256, "diversity"), (3, 7, 256, 256, "grey"), (4, 9, 256, 300, "none")):
         ints, floats = sample_params(seed, first, 200, H, W, 224, recipe)
         for b in range(200):
             i2, f2 = A.sample_params(seed, first + b, H, W, 224, recipe)
@@ -87,7 +88,8 @@ def test_oracle_identity_and_patch_layout():
 # ---------------------------------------------------------------------------------------------- GPU
 @pytest.mark.gpu
 @pytest.mark.parametrize("H,W,seed,recipe", [(256, 256, 1, "full"), (256, 256, 2, "full"), (300, 200, 3, "full"),
-                                             (224, 224, 4, "generalization"), (96, 128, 5, "full")])
+                                             (224, 224, 4, "generalization"), (96, 128, 5, "full"),
+                                             (256, 256, 6, "diversity"), (256, 256, 7, "grey"), (256, 320, 8, "none")])
 def test_kernel_is_bit_exact_against_oracle(H, W, seed, recipe):
     from touhouimageclassification_b200.augment import GpuAugment
     B = 12
@@ -159,3 +161,25 @@ def test_augmented_patches_feed_the_engine():
     assert GpuAugment(seed=3).__call__(imgs, first_sample=0).equal(patches)       # deterministic in (seed, index)
     with pytest.raises(ValueError):
         GpuAugment()(imgs.cpu())
+
+
+@pytest.mark.gpu
+def test_inference_transform_on_gpu_matches_reference_recipe():
+    """serve.preprocess_u8 == Resize((224,224)) -> ToTensor -> Normalize(dataset mean/std) (preprocess.py:73-77):
+    bit-exact against the oracle's 'none' recipe, and within 1 LSB of torchvision's own uint8 resize."""
+    TF = pytest.importorskip("torchvision.transforms.v2.functional")
+    from touhouimageclassification_b200 import serve as S
+    imgs = smooth_images(3, 256, 256, 11)
+    mean, std = [0.61, 0.55, 0.52], [0.31, 0.30, 0.29]
+    patches = S.preprocess_u8(torch.from_numpy(imgs).cuda(), mean, std)
+    A_MEAN, A_STD = A.MEAN.copy(), A.STD.copy()
+    try:
+        A.MEAN[:] = np.array(mean, np.float32)
+        A.STD[:] = np.array(std, np.float32)
+        ref_pix, ref_tok = A.augment_batch(imgs, 0, first_sample=0, recipe="none")
+    finally:
+        A.MEAN[:] = A_MEAN
+        A.STD[:] = A_STD
+    assert np.array_equal(patches.view(torch.int16).cpu().numpy().view(np.uint16), ref_tok)
+    tv = TF.resize(torch.from_numpy(imgs).permute(0, 3, 1, 2), [224, 224], antialias=True).permute(0, 2, 3, 1).numpy()
+    assert np.abs(tv.astype(int) - ref_pix.astype(int)).max() <= 1

@@ -213,3 +213,45 @@ def test_vit_l_full_size_properties(image_size, batch):
         num += (p.grad - q.grad).pow(2).sum().item()
         den += q.grad.pow(2).sum().item()
     assert (num / den) ** 0.5 < 3e-2
+
+
+# ---------------------------------------------------------------------------------------------- fp32 mode
+def test_fp32_mode_matches_golden_within_1e4(golden_dir):
+    """north_star: logits within 1e-4 relative in fp32 mode (the reference serves with no autocast, serve.py:99-101).
+    Split-bf16 GEMMs on tcgen05 + fp32 LayerNorm / GELU / softmax; golden logits come from HF fp32 on CPU."""
+    for cfg, scale, name, B, S, seed in ((TINY, 0.05, "tiny_train_step.npz", 3, 32, 1), (BASE, 0.02, "vitb16_forward.npz", 2, 224, 2)):
+        g = np.load(os.path.join(golden_dir, name))
+        m = make(cfg, scale).eval().set_precision("fp32")
+        x = O.deterministic_images(B, S, seed=seed).to(dev)
+        with torch.no_grad():
+            logits = m(x).logits
+        ref = torch.from_numpy(g["logits"]).to(dev)
+        assert logits.dtype == torch.float32
+        assert rel(logits, ref) < 1e-4, (name, rel(logits, ref))
+        assert torch.equal(logits.argmax(1).cpu(), ref.argmax(1).cpu())
+
+
+def test_fp32_mode_vitl_against_live_oracle_and_top1():
+    """ViT-L/16 at random init (sigma 0.02), N(0,1) images: fp32 mode vs the oracle in fp32 on the same GPU (TF32 off):
+    relative error < 1e-4 and top-1 agreement >= 99.9% (SURVEY Appendix D consequence 2)."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    cfg = dict(hidden_size=1024, num_hidden_layers=24, num_attention_heads=16, intermediate_size=4096, image_size=224, num_labels=120)
+    from touhouimageclassification_b200.model import ViTConfig, ViTForImageClassification
+    torch.manual_seed(1234)
+    m = ViTForImageClassification(ViTConfig(**cfg)).to(dev).eval().set_precision("fp32")
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    x = torch.randn(64, 3, 224, 224, device=dev)
+    with torch.no_grad():
+        ours = m(x).logits
+        ref = O.vit_forward(sd, x, cfg["num_attention_heads"])
+    assert rel(ours, ref) < 1e-4, rel(ours, ref)
+    assert (ours.argmax(1) == ref.argmax(1)).float().mean().item() >= 0.999
+    # weights changed -> the split copy is refreshed
+    with torch.no_grad():
+        m.classifier.bias.add_(1.0)
+        again = m(x).logits
+    assert torch.allclose(again, ours + 1.0, atol=1e-4)
+    with pytest.raises(RuntimeError):
+        m.train()
+        m(x)

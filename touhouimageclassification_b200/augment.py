@@ -18,7 +18,7 @@ from ._lib import c_i64, c_int, c_void_p
 
 IMAGENET_MEAN = (0.485, 0.456, 0.406)
 IMAGENET_STD = (0.229, 0.224, 0.225)
-RECIPES = {"full": 0, "generalization": 1}
+RECIPES = {"full": 0, "generalization": 1, "diversity": 2, "grey": 3, "none": 4}
 
 
 def sample_params(seed: int, first_sample: int, batch: int, height: int, width: int, size: int = 224,

@@ -170,4 +170,21 @@ TIC_API int tic_vit_backward(const tic_vit_config* cfg, const float* params_f32,
                       stage_end, head_only, S(stream));
 }
 
+TIC_API int64_t tic_vit_w6_elems(const tic_vit_config* cfg) {
+  if (vit_validate(cfg) != kOk) return -1;
+  return vit_w6_elems(cfg);
+}
+TIC_API int64_t tic_vit_workspace_bytes_f32(const tic_vit_config* cfg, int batch) {
+  if (vit_validate(cfg) != kOk || batch <= 0) return -1;
+  return vit_workspace_bytes_f32(cfg, batch);
+}
+TIC_API int tic_vit_prepare_w6(const tic_vit_config* cfg, const float* params_f32, void* w6_bf16, void* stream) {
+  return vit_prepare_w6(cfg, params_f32, w6_bf16, S(stream));
+}
+TIC_API int tic_vit_forward_f32(const tic_vit_config* cfg, const float* params_f32, const void* w6_bf16,
+                                const float* pixels, int batch, void* workspace, int64_t workspace_bytes, float* logits,
+                                void* stream) {
+  return vit_forward_f32(cfg, params_f32, w6_bf16, pixels, batch, workspace, workspace_bytes, logits, S(stream));
+}
+
 }  // extern "C"

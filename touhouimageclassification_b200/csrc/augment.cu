@@ -257,10 +257,16 @@ inline int round_half_even(double x) { return static_cast<int>(std::nearbyint(x)
 
 }  // namespace
 
-// recipe: 0 = full (ntrain.py:104-112), 1 = generalization only (crop + flip + erase, ntrain.py:127-134)
+// recipe: 0 = full (ntrain.py:104-112), 1 = generalization only (crop + flip + erase, :127-134), 2 = diversity only
+// (Resize + ColorJitter + RandomGrayscale, :119-126), 3 = grey only (Resize + RandomGrayscale, :97-102),
+// 4 = none (Resize only: the test / inference transform, :137-147 and utils/preprocess.py:73-77).
+// Random numbers are drawn only for the transforms a recipe contains, in pipeline order.
 int augment_sample_params(long long seed, long long first_sample, int B, int H, int W, int size, int recipe,
                           int* ints_host, float* floats_host) {
   if (B < 0 || H <= 0 || W <= 0 || size <= 0) return set_error(kErrInvalidArg, "augment_sample_params: bad sizes");
+  if (recipe < 0 || recipe > 4) return set_error(kErrInvalidArg, "augment_sample_params: unknown recipe %d", recipe);
+  const bool do_crop = recipe <= 1, do_flip = recipe <= 1, do_jitter = recipe == 0 || recipe == 2;
+  const bool do_gray = recipe == 0 || recipe == 2 || recipe == 3, do_erase = recipe <= 1;
   for (int b = 0; b < B; ++b) {
     Stream st{static_cast<uint64_t>(seed), static_cast<uint64_t>(first_sample + b), 0};
     int* I = ints_host + 16 * b;
@@ -268,7 +274,7 @@ int augment_sample_params(long long seed, long long first_sample, int B, int H, 
     const double area = static_cast<double>(H) * W;
     const double lr0 = std::log(3.0 / 4.0), lr1 = std::log(4.0 / 3.0);
     int top = 0, left = 0, h = H, w = W;
-    bool found = false;
+    bool found = !do_crop;  // Resize-only recipes use the whole frame
     for (int t = 0; t < 10 && !found; ++t) {
       const double target = area * st.uniform(0.08, 1.0);
       const double aspect = std::exp(st.uniform(lr0, lr1));
@@ -281,23 +287,24 @@ int augment_sample_params(long long seed, long long first_sample, int B, int H, 
         found = true;
       }
     }
-    if (!found) {
+    if (!found && do_crop) {
       const double in_ratio = static_cast<double>(W) / static_cast<double>(H);
       if (in_ratio < 3.0 / 4.0) { w = W; h = round_half_even(w / (3.0 / 4.0)); }
       else if (in_ratio > 4.0 / 3.0) { h = H; w = round_half_even(h * (4.0 / 3.0)); }
       else { w = W; h = H; }
       top = (H - h) / 2; left = (W - w) / 2;
     }
-    const int flip = st.uniform(0.0, 1.0) < 0.5 ? 1 : 0;
+    const int flip = do_flip ? (st.uniform(0.0, 1.0) < 0.5 ? 1 : 0) : 0;
     int perm[4] = {0, 1, 2, 3};
-    for (int i = 3; i > 0; --i) {
+    for (int i = 3; i > 0 && do_jitter; --i) {
       const int j = st.randint(i + 1);
       const int tmp = perm[i]; perm[i] = perm[j]; perm[j] = tmp;
     }
-    const double bb = st.uniform(0.8, 1.2), cc = st.uniform(0.8, 1.2), ss = st.uniform(0.8, 1.2), hh = st.uniform(-0.1, 0.1);
-    int gray = st.uniform(0.0, 1.0) < 0.2 ? 1 : 0;
+    double bb = 1.0, cc = 1.0, ss = 1.0, hh = 0.0;
+    if (do_jitter) { bb = st.uniform(0.8, 1.2); cc = st.uniform(0.8, 1.2); ss = st.uniform(0.8, 1.2); hh = st.uniform(-0.1, 0.1); }
+    const int gray = do_gray ? (st.uniform(0.0, 1.0) < 0.2 ? 1 : 0) : 0;
     int ei = 0, ej = 0, eh = 0, ew = 0;
-    if (st.uniform(0.0, 1.0) < 0.5) {
+    if (do_erase && st.uniform(0.0, 1.0) < 0.5) {
       const double el0 = std::log(0.3), el1 = std::log(3.3);
       for (int t = 0; t < 10; ++t) {
         const double ea = static_cast<double>(size) * size * st.uniform(0.02, 0.33);
@@ -311,8 +318,7 @@ int augment_sample_params(long long seed, long long first_sample, int B, int H, 
         break;
       }
     }
-    int jitter_on = 1;
-    if (recipe == 1) { jitter_on = 0; gray = 0; }
+    const int jitter_on = do_jitter ? 1 : 0;
     const int vals[16] = {top, left, h, w, flip, perm[0], perm[1], perm[2], perm[3], gray, ei, ej, eh, ew, jitter_on, 0};
     for (int i = 0; i < 16; ++i) I[i] = vals[i];
     F[0] = static_cast<float>(bb); F[1] = static_cast<float>(cc); F[2] = static_cast<float>(ss); F[3] = static_cast<float>(hh);

@@ -61,6 +61,7 @@ struct GemmParams {
   long long ldaux;
   int aux_int;  // kEpiF32PosEmbed: patches per image (P)
   float* colsum;  // kEpiBf16DGelu: optional, accumulates column sums of the bf16 output (bias gradient)
+  int exact;      // fp32 verification mode: kEpiF32Resid / kEpiF32PosEmbed add without the bf16 rounding of autocast
 };
 
 template <bool A_MN, bool B_MN, int EPI, int NCTA>
@@ -303,8 +304,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             } else if constexpr (EPI == kEpiF32Resid) {
               // bf16 GEMM output added to the fp32 residual stream (Appendix B).
               const float4 x = auxf[i];
+              if (!p.exact) { a.x = round_bf16(a.x); a.y = round_bf16(a.y); a.z = round_bf16(a.z); a.w = round_bf16(a.w); }
               *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<long long>(row) * p.ldo + col) =
-                  make_float4(round_bf16(a.x) + x.x, round_bf16(a.y) + x.y, round_bf16(a.z) + x.z, round_bf16(a.w) + x.w);
+                  make_float4(a.x + x.x, a.y + x.y, a.z + x.z, a.w + x.w);
+            } else if constexpr (EPI == kEpiF32Gelu) {
+              *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<long long>(row) * p.ldo + col) =
+                  make_float4(gelu_erf(a.x), gelu_erf(a.y), gelu_erf(a.z), gelu_erf(a.w));
             } else if constexpr (EPI == kEpiF32) {
               *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<long long>(row) * p.ldo + col) = a;
             } else if constexpr (EPI == kEpiF32Atomic) {
@@ -315,9 +320,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
               const int P = p.aux_int;
               const int img = row / P, pidx = row - img * P;
               const float4 x = auxf[i];
+              if (!p.exact) { a.x = round_bf16(a.x); a.y = round_bf16(a.y); a.z = round_bf16(a.z); a.w = round_bf16(a.w); }
               *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) +
                                          (static_cast<long long>(img) * (P + 1) + 1 + pidx) * p.ldo + col) =
-                  make_float4(round_bf16(a.x) + x.x, round_bf16(a.y) + x.y, round_bf16(a.z) + x.z, round_bf16(a.w) + x.w);
+                  make_float4(a.x + x.x, a.y + x.y, a.z + x.z, a.w + x.w);
             }
           }
           if constexpr (EPI == kEpiBf16DGelu) {
@@ -410,7 +416,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cu
 // B: K-major => [N, K] row-major with pitch ldb; MN-major => [K, N] row-major with pitch ldb.
 int gemm_bf16(const void* A, long long lda, bool a_mn, const void* B, long long ldb, bool b_mn, int M, int N, int K,
               int epilogue, void* out, long long ldo, void* out2, long long ldo2, const float* bias, const void* aux,
-              long long ldaux, int aux_int, int splits, cudaStream_t stream, float* colsum) {
+              long long ldaux, int aux_int, int splits, cudaStream_t stream, float* colsum, bool exact) {
   if (M <= 0 || N <= 0 || K <= 0) return set_error(kErrInvalidArg, "gemm: empty problem %dx%dx%d", M, N, K);
   if (N % 8 != 0) return set_error(kErrInvalidArg, "gemm: N=%d must be a multiple of 8", N);
   if ((lda % 8) || (ldb % 8)) return set_error(kErrInvalidArg, "gemm: operand pitches must be multiples of 8 elements");
@@ -439,14 +445,14 @@ int gemm_bf16(const void* A, long long lda, bool a_mn, const void* B, long long 
   GemmParams p;
   p.M = M; p.N = N; p.K = K; p.splits = splits;
   p.out = out; p.ldo = ldo; p.out2 = out2; p.ldo2 = ldo2;
-  p.bias = bias; p.aux = aux; p.ldaux = ldaux; p.aux_int = aux_int; p.colsum = colsum;
+  p.bias = bias; p.aux = aux; p.ldaux = ldaux; p.aux_int = aux_int; p.colsum = colsum; p.exact = exact ? 1 : 0;
 
-  static const char* kNames[2][2][7] = {
-      {{"gemm_fwd_bf16", "gemm_fwd_gelu", "gemm_fwd_resid", "gemm_fwd_x", "gemm_fwd_f32", "gemm_fwd_x", "gemm_fwd_posemb"},
-       {"gemm_dgrad_bf16", "gemm_dgrad_x", "gemm_dgrad_x", "gemm_dgrad_dgelu", "gemm_dgrad_f32", "gemm_dgrad_x", "gemm_dgrad_x"}},
-      {{"gemm_x", "gemm_x", "gemm_x", "gemm_x", "gemm_x", "gemm_x", "gemm_x"},
-       {"gemm_wgrad_x", "gemm_wgrad_x", "gemm_wgrad_x", "gemm_wgrad_x", "gemm_wgrad_f32", "gemm_wgrad_atomic", "gemm_wgrad_x"}}};
-  ProfScope prof(epilogue >= 0 && epilogue < 7 ? kNames[a_mn][b_mn][epilogue] : "gemm_x", 2.0 * M * N * K,
+  static const char* kNames[2][2][8] = {
+      {{"gemm_fwd_bf16", "gemm_fwd_gelu", "gemm_fwd_resid", "gemm_fwd_x", "gemm_fwd_f32", "gemm_fwd_x", "gemm_fwd_posemb", "gemm_fwd_gelu_f32"},
+       {"gemm_dgrad_bf16", "gemm_dgrad_x", "gemm_dgrad_x", "gemm_dgrad_dgelu", "gemm_dgrad_f32", "gemm_dgrad_x", "gemm_dgrad_x", "gemm_dgrad_x"}},
+      {{"gemm_x", "gemm_x", "gemm_x", "gemm_x", "gemm_x", "gemm_x", "gemm_x", "gemm_x"},
+       {"gemm_wgrad_x", "gemm_wgrad_x", "gemm_wgrad_x", "gemm_wgrad_x", "gemm_wgrad_f32", "gemm_wgrad_atomic", "gemm_wgrad_x", "gemm_wgrad_x"}}};
+  ProfScope prof(epilogue >= 0 && epilogue < 8 ? kNames[a_mn][b_mn][epilogue] : "gemm_x", 2.0 * M * N * K,
                  2.0 * (static_cast<double>(M) * K + static_cast<double>(N) * K) +
                      static_cast<double>(M) * N * ((epilogue == kEpiBf16 || epilogue == kEpiBf16DGelu) ? 2 : 4),
                  stream);
@@ -458,6 +464,7 @@ int gemm_bf16(const void* A, long long lda, bool a_mn, const void* B, long long 
   TIC_GEMM_CASE(false, false, kEpiF32Resid)
   TIC_GEMM_CASE(false, false, kEpiF32)
   TIC_GEMM_CASE(false, false, kEpiF32PosEmbed)
+  TIC_GEMM_CASE(false, false, kEpiF32Gelu)
   // dgrad (K-major x MN-major)
   TIC_GEMM_CASE(false, true, kEpiBf16)
   TIC_GEMM_CASE(false, true, kEpiBf16DGelu)

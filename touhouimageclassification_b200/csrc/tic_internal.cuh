@@ -27,12 +27,13 @@ enum Epilogue : int {
   kEpiF32 = 4,          // out f32 = acc (+bias)
   kEpiF32Atomic = 5,    // out f32 += acc (split-K partial, red.global.add)
   kEpiF32PosEmbed = 6,  // patch embedding rows: see tic_b200.h
+  kEpiF32Gelu = 7,      // out f32 = gelu_erf(acc + bias), exact erff (fp32 verification mode)
 };
 
 // gemm_tcgen05.cu
 int gemm_bf16(const void* A, long long lda, bool a_mn, const void* B, long long ldb, bool b_mn, int M, int N, int K,
               int epilogue, void* out, long long ldo, void* out2, long long ldo2, const float* bias, const void* aux,
-              long long ldaux, int aux_int, int splits, cudaStream_t stream, float* colsum = nullptr);
+              long long ldaux, int aux_int, int splits, cudaStream_t stream, float* colsum = nullptr, bool exact = false);
 
 // layernorm.cu
 int layernorm_fwd(const float* x, long long ldx, const float* gamma, const float* beta, float eps, int rows, int D,
@@ -104,5 +105,13 @@ int vit_forward(const tic_vit_config* c, const float* P32, const void* P16, cons
 int vit_backward(const tic_vit_config* c, const float* P32, const void* P16, int B, void* workspace,
                  long long workspace_bytes, const float* dlogits, float* G, int stage_begin, int stage_end,
                  int head_only, cudaStream_t st);
+
+
+// fp32_path.cu: fp32-accurate inference (split-bf16 GEMMs on tcgen05, fp32 everything else)
+long long vit_w6_elems(const tic_vit_config* c);
+long long vit_workspace_bytes_f32(const tic_vit_config* c, int B);
+int vit_prepare_w6(const tic_vit_config* c, const float* P32, void* w6, cudaStream_t st);
+int vit_forward_f32(const tic_vit_config* c, const float* P32, const void* w6, const float* pixels, int B,
+                    void* workspace, long long workspace_bytes, float* logits, cudaStream_t st);
 
 }  // namespace tic

@@ -189,7 +189,12 @@ class ViTForImageClassification(nn.Module):
         self._workspaces = {}
         self._ws_generation = 0
         self._lock = threading.RLock()
+        # "bf16": tensor-core engine with autocast rounding points (training, ntrain.py:241 bf16-mixed).
+        # "fp32": split-bf16 GEMMs, fp32 everything else -- the reference's no-autocast inference (serve.py:99-101);
+        #         forward only, selected with set_precision("fp32").
         self.precision = "bf16"
+        self._w6 = None
+        self._w6_key = None
 
     # ---- structure ------------------------------------------------------------------------------
     def _build_tree(self, params):
@@ -267,6 +272,8 @@ class ViTForImageClassification(nn.Module):
         self._arena = arena
         self._shadow = None
         self._shadow_key = None
+        self._w6 = None
+        self._w6_key = None
         self._grad_arena = None
         self._workspaces = {}
 
@@ -302,6 +309,63 @@ class ViTForImageClassification(nn.Module):
                                                         c_i64(self._total), _stream()))
             self._shadow_key = key
 
+    def set_precision(self, precision: str):
+        """``"bf16"`` (default) or ``"fp32"`` (inference only; logits within 1e-4 relative of the fp32 reference)."""
+        if precision not in ("bf16", "fp32"):
+            raise ValueError(f"precision must be 'bf16' or 'fp32', got {precision!r}")
+        self.precision = precision
+        if precision == "bf16":
+            self._w6 = None
+            self._w6_key = None
+        return self
+
+    def _refresh_w6(self):
+        """Split weights for the fp32 mode: every GEMM weight as three bf16 terms laid out [N, 6K]."""
+        if not self._arena_ok():
+            self._repack()
+        lib = _lib.load()
+        key = self._version_key()
+        c = self.config.to_c()
+        if self._w6 is None or self._w6.device != self._arena.device:
+            lib.tic_vit_w6_elems.restype = ctypes.c_int64
+            n = lib.tic_vit_w6_elems(ctypes.byref(c))
+            if n < 0:
+                _lib.check(1)
+            self._w6 = torch.empty(n, dtype=torch.bfloat16, device=self._arena.device)
+            self._w6_key = None
+        if key != self._w6_key:
+            _lib.check(lib.tic_vit_prepare_w6(ctypes.byref(c), c_void_p(self._arena.data_ptr()),
+                                              c_void_p(self._w6.data_ptr()), _stream()))
+            self._w6_key = key
+
+    def engine_forward_f32(self, pixel_values: torch.Tensor) -> torch.Tensor:
+        """fp32-mode forward (tic_vit_forward_f32): fp32 NCHW pixels -> fp32 logits."""
+        with self._lock:
+            self._check_input(pixel_values)
+            self._refresh_w6()
+            x = pixel_values.detach()
+            if x.dtype != torch.float32 or not x.is_contiguous():
+                x = x.float().contiguous()
+            batch = x.shape[0]
+            lib = _lib.load()
+            c = self.config.to_c()
+            key = (batch, "f32")
+            ws = self._workspaces.get(key)
+            if ws is None or ws.device != self._arena.device:
+                lib.tic_vit_workspace_bytes_f32.restype = ctypes.c_int64
+                nbytes = lib.tic_vit_workspace_bytes_f32(ctypes.byref(c), c_int(batch))
+                if nbytes < 0:
+                    _lib.check(1)
+                for k in [k for k in self._workspaces if k[1] == "f32"]:
+                    del self._workspaces[k]
+                ws = torch.empty(nbytes, dtype=torch.uint8, device=self._arena.device)
+                self._workspaces[key] = ws
+            logits = torch.empty((batch, self.config.num_labels), dtype=torch.float32, device=self._arena.device)
+            _lib.check(lib.tic_vit_forward_f32(
+                ctypes.byref(c), c_void_p(self._arena.data_ptr()), c_void_p(self._w6.data_ptr()), c_void_p(x.data_ptr()),
+                c_int(batch), c_void_p(ws.data_ptr()), c_i64(ws.numel()), c_void_p(logits.data_ptr()), _stream()))
+            return logits
+
     def mark_shadow_fresh(self):
         """Called by the fused optimizer, which writes the shadow itself."""
         self._shadow_key = self._version_key()
@@ -326,7 +390,7 @@ class ViTForImageClassification(nn.Module):
             if nbytes < 0:
                 _lib.check(1)
             if training:  # keep a single training workspace alive (tens of GB at batch 256)
-                for k in [k for k in self._workspaces if k[1]]:
+                for k in [k for k in self._workspaces if k[1] is True]:
                     del self._workspaces[k]
             ws = torch.empty(nbytes, dtype=torch.uint8, device=self._arena.device)
             self._workspaces[key] = ws
@@ -403,7 +467,12 @@ class ViTForImageClassification(nn.Module):
         self._check_input(pixel_values)
         params = self._params_in_order()
         needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
-        if needs_grad:
+        if self.precision == "fp32":
+            if needs_grad:
+                raise RuntimeError("precision='fp32' is the inference mode (serve.py:99-101); the reference never "
+                                   "trains in fp32 -- use torch.no_grad() / requires_grad_(False), or set_precision('bf16')")
+            logits = self.engine_forward_f32(pixel_values)
+        elif needs_grad:
             logits = _ViTFunction.apply(self, pixel_values, *params)
         else:
             logits = self.engine_forward(pixel_values, training=False)

@@ -39,8 +39,11 @@ def extract_state_dict(ckpt):
     return ckpt
 
 
-def load_model(model_type: str, num_classes: int, weights_path: str = None, device: str = 'cuda'):
-    """serve.load_model (serve.py:47-81): tuple checkpoints -> ``[0]``, strict ``load_state_dict``, ``.to(device)``."""
+def load_model(model_type: str, num_classes: int, weights_path: str = None, device: str = 'cuda',
+               precision: str = 'bf16'):
+    """serve.load_model (serve.py:47-81): tuple checkpoints -> ``[0]``, strict ``load_state_dict``, ``.to(device)``.
+    ``precision='fp32'`` selects the fp32-accurate engine (what the reference's no-autocast forward computes,
+    serve.py:99-101) instead of the bf16 tensor-core one."""
     model_type = model_type.lower().replace('_', '-')
     model = get_model(model_type, num_classes)
     if weights_path is None:
@@ -48,6 +51,7 @@ def load_model(model_type: str, num_classes: int, weights_path: str = None, devi
     ckpt = torch.load(weights_path, map_location="cpu", weights_only=False)
     model.load_state_dict(extract_state_dict(ckpt))
     model.to(device)
+    model.set_precision(precision)
     return model
 
 
@@ -66,6 +70,34 @@ def serve(model, image_tensor, class_to_idx, device: str = 'cuda'):
 
 
 _predict_lock = threading.Lock()
+
+
+def preprocess_u8(images_u8: torch.Tensor, mean, std, size: int = 224) -> torch.Tensor:
+    """The reference's inference transform (``utils/preprocess.py:73-77`` [a23]: ``Resize((224,224))`` -> ``ToTensor`` ->
+    ``Normalize(mean, std)`` with the dataset statistics from ``meta_mean_std.pth``) on the GPU: uint8 NHWC batch ->
+    bf16 patch rows for ``engine_forward(patches=...)``. Same fused kernel as the training augmentation, recipe "none"."""
+    from .augment import GpuAugment
+    mean = [float(m) for m in mean]
+    std = [float(s) for s in std]
+    return GpuAugment(seed=0, size=size, recipe="none", mean=mean, std=std)(images_u8, first_sample=0)
+
+
+def predict_batch_u8(model: ViTForImageClassification, images_u8: torch.Tensor, mean, std, idx_to_class=None,
+                     max_batch_size: int = 1024):
+    """``serve_batch`` (runtime.py:235-251) end to end on the device: raw uint8 NHWC thumbnails in, (class, confidence)
+    out -- resize + normalise + patchify in one kernel, bf16 engine forward, softmax/max, one host copy per chunk."""
+    model.eval()
+    results = []
+    with torch.no_grad(), _predict_lock:
+        for i in range(0, images_u8.shape[0], max_batch_size):
+            chunk = images_u8[i:i + max_batch_size].to(model._arena.device, non_blocking=True)
+            logits = model.engine_forward(patches=preprocess_u8(chunk, mean, std, model.config.image_size))
+            prob = torch.softmax(logits, dim=1)
+            conf, idx = torch.max(prob, 1)
+            for c, k in torch.stack([conf, idx.to(conf.dtype)], 1).cpu().tolist():
+                k = int(k)
+                results.append((idx_to_class[k] if idx_to_class is not None else k, c))
+    return results
 
 
 def predict_batch(model: ViTForImageClassification, image_batch: torch.Tensor, idx_to_class=None,
