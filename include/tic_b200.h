@@ -103,6 +103,14 @@ TIC_API int tic_attention_bwd(const void* q, const void* k, const void* v, int64
                               const void* dout, int64_t lddo, const float* lse, float* delta_scratch, void* dq, void* dk,
                               void* dv, int64_t lddqkv, int B, int N, int H, int head_dim, float scale, void* stream);
 
+/* Same backward that also ACCUMULATES the column sums of dq | dk | dv into qkv_bias_grad (fp32 [3 * H * 64]): the bias
+ * gradient of the fused QKV Linear (modeling_vit.py:216-230 [a5]). For N <= 256 the whole backward (delta, dQ, dK, dV,
+ * bias gradient) is ONE kernel per call and delta_scratch is not touched. */
+TIC_API int tic_attention_bwd_bias(const void* q, const void* k, const void* v, int64_t ld, const void* o, int64_t ldo,
+                                   const void* dout, int64_t lddo, const float* lse, float* delta_scratch, void* dq,
+                                   void* dk, void* dv, int64_t lddqkv, float* qkv_bias_grad, int B, int N, int H,
+                                   int head_dim, float scale, void* stream);
+
 /* ---- classifier head and fused softmax cross-entropy ----------------------------------------------
  * tic_head_fwd: logits[B,C] = h[B,D] W[C,D]^T + b (classifier, modeling_vit.py:641-642 [a11]).
  * tic_softmax_xent: F.cross_entropy forward + backward in one launch, integer targets (finetune.py:61

@@ -22,3 +22,6 @@ fl = 4.0 * B * H * N * N * 64
 print(f"fwd B{B} N{N} H{H}: {t:.3f} ms  {fl / t / 1e9:.0f} TFLOP/s (useful)")
 t = timeit(lambda: ops.attention_bwd(qkv, ctx, dctx, lse, B, N, H))
 print(f"bwd B{B} N{N} H{H}: {t:.3f} ms  {2.5 * fl / t / 1e9:.0f} TFLOP/s (useful, 5 matmuls)")
+bg = torch.zeros(3 * D, device="cuda")
+t = timeit(lambda: ops.attention_bwd(qkv, ctx, dctx, lse, B, N, H, bias_grad=bg))
+print(f"bwd+bias B{B} N{N} H{H}: {t:.3f} ms  {2.5 * fl / t / 1e9:.0f} TFLOP/s (useful, 5 matmuls)")

@@ -131,7 +131,8 @@ def test_layernorm_eps_is_1e_12_not_fixed():
     assert torch.allclose(yf, torch.full_like(yf, 0.25))
 
 
-@pytest.mark.parametrize("B,N,H", [(2, 197, 12), (2, 577, 4), (2, 64, 2), (1, 1, 1), (2, 130, 3), (1, 5, 2)])
+@pytest.mark.parametrize("B,N,H", [(2, 197, 12), (2, 577, 4), (2, 64, 2), (1, 1, 1), (2, 130, 3), (1, 5, 2), (3, 256, 2),
+                                   (2, 128, 1), (2, 129, 2), (2, 192, 2), (2, 193, 1), (2, 65, 2), (1, 257, 2), (64, 197, 16)])
 def test_attention_fwd_bwd(B, N, H):
     from touhouimageclassification_b200 import ops
     D = H * 64
@@ -145,6 +146,7 @@ def test_attention_fwd_bwd(B, N, H):
     dctx = torch.randn(B * N, D, device=dev).bfloat16()
     ref.backward(dctx.float())
     dqkv = ops.attention_bwd(qkv, ctx, dctx, lse, B, N, H)
+    assert torch.isfinite(dqkv.float()).all()
     dq, dk, dv = dqkv.float().split(D, dim=1)
     for ours, t in ((dq, q), (dk, k), (dv, v)):
         r = t.grad.transpose(1, 2).reshape(B * N, D)
@@ -152,6 +154,12 @@ def test_attention_fwd_bwd(B, N, H):
             assert (ours - r).abs().max() < 2e-2
         else:
             assert rel(ours, r) < 6e-3
+    # the fused QKV bias gradient accumulates the column sums of the bf16 dqkv it wrote, and dqkv itself is unchanged
+    bg = torch.full((3 * D,), 0.5, device=dev)
+    dqkv2 = ops.attention_bwd(qkv, ctx, dctx, lse, B, N, H, bias_grad=bg)
+    assert torch.equal(dqkv2, dqkv)
+    want = dqkv.float().sum(0) + 0.5
+    assert (bg - want).abs().max() <= 1e-4 * max(1.0, want.abs().max().item()) + 1e-5 * B * N
 
 
 def test_softmax_xent_hard_and_soft():

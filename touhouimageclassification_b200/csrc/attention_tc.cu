@@ -71,7 +71,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 4) {
-    if (lane == 0) {
+    if (elect_one()) {  // one issuing thread the compiler can keep on the uniform datapath
       constexpr uint32_t idesc_s = make_idesc_bf16(AT_QT, KVB, false, false);
       constexpr uint32_t idesc_o = make_idesc_bf16(AT_QT, AT_HD, false, true);
       mbar_arrive_expect_tx(bar_q, AT_QT * 128);
@@ -302,7 +302,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_r1, const __grid_const
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 4) {
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc_ss = make_idesc_bf16(AT_QT, AB_CB, false, false);
       constexpr uint32_t idesc_ts = make_idesc_bf16(AT_QT, AT_HD, false, true);
       mbar_arrive_expect_tx(bar_rows, 2 * AT_QT * 128);
@@ -487,10 +487,16 @@ int attention_fwd_tc(const void* q, const void* k, const void* v, long long ld, 
 
 int attention_bwd_tc(const void* q, const void* k, const void* v, long long ld, const void* o, long long ldo,
                      const void* dout, long long lddo, const float* lse, float* delta, void* dq, void* dk, void* dv,
-                     long long lddqkv, int B, int N, int H, int head_dim, float scale, cudaStream_t stream) {
+                     long long lddqkv, int B, int N, int H, int head_dim, float scale, cudaStream_t stream,
+                     float* bias_grad) {
   if (head_dim != AT_HD) return set_error(kErrUnsupported, "attention: head_dim=%d (only 64 is supported)", head_dim);
   if (B <= 0 || N <= 0) return kOk;
-  if ((ld % 8) || (lddo % 8) || (lddqkv % 8)) return set_error(kErrInvalidArg, "attention_bwd: pitches must be multiples of 8");
+  if ((ld % 8) || (lddo % 8) || (lddqkv % 8) || (ldo % 8))
+    return set_error(kErrInvalidArg, "attention_bwd: pitches must be multiples of 8");
+  if (N <= 256) {  // whole head in shared memory: one fused kernel (delta, dQ, dK, dV, QKV bias gradient)
+    ProfScope prof("attention_bwd", 10.0 * B * H * static_cast<double>(N) * N * AT_HD, 16.0 * B * H * static_cast<double>(N) * AT_HD, stream);
+    return attention_bwd_fused(q, k, v, ld, o, ldo, dout, lddo, lse, dq, dk, dv, lddqkv, bias_grad, B, N, H, scale, stream);
+  }
   ProfScope prof("attention_bwd", 10.0 * B * H * static_cast<double>(N) * N * AT_HD, 16.0 * B * H * static_cast<double>(N) * AT_HD, stream);
   int rc = attention_delta(o, ldo, dout, lddo, delta, B, N, H, stream);
   if (rc) return rc;
@@ -498,7 +504,14 @@ int attention_bwd_tc(const void* q, const void* k, const void* v, long long ld, 
   rc = launch_bwd<false>(q, dout, ld, lddo, k, v, ld, ld, lse, delta, dq, nullptr, lddqkv, B, N, H, scale, stream);
   if (rc) return rc;
   // dK / dV: rows = keys (K, V), columns = queries (Q, dO)
-  return launch_bwd<true>(k, v, ld, ld, q, dout, ld, lddo, lse, delta, dk, dv, lddqkv, B, N, H, scale, stream);
+  rc = launch_bwd<true>(k, v, ld, ld, q, dout, ld, lddo, lse, delta, dk, dv, lddqkv, B, N, H, scale, stream);
+  if (rc || bias_grad == nullptr) return rc;
+  const int Dm = H * AT_HD;
+  rc = colsum_bf16(dq, lddqkv, B * N, Dm, bias_grad, stream);
+  if (rc) return rc;
+  rc = colsum_bf16(dk, lddqkv, B * N, Dm, bias_grad + Dm, stream);
+  if (rc) return rc;
+  return colsum_bf16(dv, lddqkv, B * N, Dm, bias_grad + 2 * Dm, stream);
 }
 
 }  // namespace tic

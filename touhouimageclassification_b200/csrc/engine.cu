@@ -306,13 +306,12 @@ int vit_backward(const tic_vit_config* c, const float* P32, const void* P16v, in
                         0, pick_splits(D, D, M), st));
       // attention core
       TIC_TRY(attention_bwd_tc(qkv, qkv + D, qkv + 2 * D, 3 * D, ctx, D, dctx, D, lse, delta, dqkv, dqkv + D, dqkv + 2 * D,
-                            3 * D, B, N, H, 64, scale, st));
+                            3 * D, B, N, H, 64, scale, st, g + L.qkv_b));  // + QKV bias gradient = colsum(dqkv)
       // fused QKV projection
       TIC_TRY(gemm_bf16(dqkv, 3 * D, false, p16 + L.qkv_w, D, true, M, D, 3 * D, kEpiBf16, dh, D, nullptr, 0, nullptr,
                         nullptr, 0, 0, 1, st));
       TIC_TRY(gemm_bf16(dqkv, 3 * D, true, h1, D, true, 3 * D, D, M, kEpiF32Atomic, g + L.qkv_w, D, nullptr, 0, nullptr,
                         nullptr, 0, 0, pick_splits(3 * D, D, M), st));
-      TIC_TRY(colsum_bf16(dqkv, 3 * D, M, 3 * D, g + L.qkv_b, st));
       // layernorm_before + residual
       // dx of layer l's input == gradient of layer (l-1)'s output: its column sums are that layer's fc2 bias gradient
       TIC_TRY(layernorm_bwd(dh, D, x_in, D, mean1, rstd1, p32 + L.ln1_w, dx, D, M, D, dx, D, l > 0 ? dxb : nullptr, D,

@@ -127,7 +127,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 
   if (warp == 8) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       auto load = [&](void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
@@ -168,7 +168,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     }
   } else if (warp == 9) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0 && cta_rank == 0) {
+    if (cta_rank == 0 && elect_one()) {
       constexpr uint32_t idesc = make_idesc_bf16(C::TILE_M, BN, A_MN, B_MN);
       // K-major SW128: 8-row atoms 1024 B apart (SBO); LBO unused.
       // MN-major SW128: atoms of 64 (MN) x 8 (K); next 8 k-rows at SBO = 1024 B, next 64-wide MN chunk at

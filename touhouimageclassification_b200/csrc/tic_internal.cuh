@@ -82,9 +82,17 @@ int augment_patchify(const void* images_u8, int B, int H, int W, const int* ints
 int attention_fwd_tc(const void* q, const void* k, const void* v, long long ld, void* o, long long ldo, float* lse,
                      int B, int N, int H, int head_dim, float scale, cudaStream_t stream);
 
+// bias_grad (optional, fp32 [3 * H * 64] = q | k | v) ACCUMULATES the column sums of dq / dk / dv (QKV bias gradient).
+// N <= 256 runs the single fused kernel of attention_bwd_fused.cu (delta is not used); longer sequences run the
+// split dQ / dKdV kernels.
 int attention_bwd_tc(const void* q, const void* k, const void* v, long long ld, const void* o, long long ldo,
                      const void* dout, long long lddo, const float* lse, float* delta, void* dq, void* dk, void* dv,
-                     long long lddqkv, int B, int N, int H, int head_dim, float scale, cudaStream_t stream);
+                     long long lddqkv, int B, int N, int H, int head_dim, float scale, cudaStream_t stream,
+                     float* bias_grad = nullptr);
+// attention_bwd_fused.cu
+int attention_bwd_fused(const void* q, const void* k, const void* v, long long ld, const void* o, long long ldo,
+                        const void* dout, long long lddo, const float* lse, void* dq, void* dk, void* dv, long long ldg,
+                        float* bias_grad, int B, int N, int H, float scale, cudaStream_t stream);
 int attention_delta(const void* o, long long ldo, const void* dout, long long lddo, float* delta, int B, int N, int H,
                     cudaStream_t stream);
 

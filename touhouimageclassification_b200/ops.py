@@ -102,16 +102,25 @@ def attention_fwd(qkv, B, N, H, scale=0.125, need_lse=True):
     return ctx, lse
 
 
-def attention_bwd(qkv, ctx, dctx, lse, B, N, H, scale=0.125):
+def attention_bwd(qkv, ctx, dctx, lse, B, N, H, scale=0.125, bias_grad=None):
+    """dqkv [B*N, 3D] bf16. ``bias_grad`` (fp32 [3D], optional) accumulates the column sums of dqkv (QKV bias gradient)."""
     _require_cuda(qkv, ctx, dctx, lse)
     D = H * 64
     dqkv = torch.empty_like(qkv)
     delta = torch.empty((B, H, N), device=qkv.device, dtype=torch.float32)
     base, dbase = qkv.data_ptr(), dqkv.data_ptr()
-    _lib.check(_lib.load().tic_attention_bwd(c_void_p(base), c_void_p(base + 2 * D), c_void_p(base + 4 * D), c_i64(3 * D),
-                                             _p(ctx), c_i64(D), _p(dctx), c_i64(D), _p(lse), _p(delta), c_void_p(dbase),
-                                             c_void_p(dbase + 2 * D), c_void_p(dbase + 4 * D), c_i64(3 * D), c_int(B),
-                                             c_int(N), c_int(H), c_int(64), c_float(scale), _s()))
+    if bias_grad is None:
+        _lib.check(_lib.load().tic_attention_bwd(c_void_p(base), c_void_p(base + 2 * D), c_void_p(base + 4 * D), c_i64(3 * D),
+                                                 _p(ctx), c_i64(D), _p(dctx), c_i64(D), _p(lse), _p(delta), c_void_p(dbase),
+                                                 c_void_p(dbase + 2 * D), c_void_p(dbase + 4 * D), c_i64(3 * D), c_int(B),
+                                                 c_int(N), c_int(H), c_int(64), c_float(scale), _s()))
+    else:
+        assert bias_grad.dtype == torch.float32 and bias_grad.numel() == 3 * D and bias_grad.is_cuda
+        _lib.check(_lib.load().tic_attention_bwd_bias(c_void_p(base), c_void_p(base + 2 * D), c_void_p(base + 4 * D),
+                                                      c_i64(3 * D), _p(ctx), c_i64(D), _p(dctx), c_i64(D), _p(lse), _p(delta),
+                                                      c_void_p(dbase), c_void_p(dbase + 2 * D), c_void_p(dbase + 4 * D),
+                                                      c_i64(3 * D), _p(bias_grad), c_int(B), c_int(N), c_int(H), c_int(64),
+                                                      c_float(scale), _s()))
     return dqkv
 
 
