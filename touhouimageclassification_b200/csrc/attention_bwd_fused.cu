@@ -23,6 +23,8 @@
 // TMEM (512 columns): S[2] 0-127 | dP[2] 128-255 | dV 256-319 | dK 320-383 | dQ[2 query tiles] 384-511.
 #include "tic_internal.cuh"
 
+#include <cstdlib>
+
 namespace tic {
 namespace {
 
@@ -32,7 +34,10 @@ constexpr int FB_HD = 64;
 constexpr float FB_LOG2E = 1.4426950408889634f;
 constexpr int FB_OPER_BYTES = FB_ROWS * 128;   // 32 KB per operand
 constexpr int FB_STAGE_BYTES = 2 * 128 * 128;  // one dS^T tile: 2 query chunks x 128 key rows x 128 B
-constexpr int FB_SMEM = 4 * FB_OPER_BYTES + 2 * FB_STAGE_BYTES + 2 * FB_ROWS * 4 + 128 + 1024;
+constexpr int FB_OUT_BYTES = 8 * 2 * 2048;       // per compute warp: two 32-row x 64-byte output tiles for the TMA stores
+constexpr int FB_SMEM_USED = 4 * FB_OPER_BYTES + 2 * FB_STAGE_BYTES + FB_OUT_BYTES + 2 * FB_ROWS * 4 + 64;
+constexpr int FB_SMEM = 232448;                  // everything the SM has; the slack (960 B) absorbs the 1024-byte alignment
+static_assert(FB_SMEM_USED <= FB_SMEM, "attention_bwd_fused: shared memory budget");
 constexpr uint32_t FB_COL_DP = 128, FB_COL_DV = 256, FB_COL_DK = 320, FB_COL_DQ = 384;
 
 TIC_DEVINL void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
@@ -69,20 +74,28 @@ TIC_DEVINL float warp_colsum32(float (&v)[32], int lane) {
 __global__ void __launch_bounds__(FB_THREADS, 1)
 attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                       const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
-                      const __grid_constant__ CUtensorMap tm_o, const float* __restrict__ lse, __nv_bfloat16* __restrict__ dq,
-                      __nv_bfloat16* __restrict__ dk, __nv_bfloat16* __restrict__ dv, long long ldg,
-                      float* __restrict__ bias_grad, int N, int H, float scale) {
+                      const __grid_constant__ CUtensorMap tm_o, const __grid_constant__ CUtensorMap tm_dq,
+                      const __grid_constant__ CUtensorMap tm_dk, const __grid_constant__ CUtensorMap tm_dv,
+                      const float* __restrict__ lse, float* __restrict__ bias_grad, int bias_mask, int N, int H, int num_items, float scale,
+                      long long* __restrict__ trace) {
+  // trace (dev tool, normally NULL): clock64 stamps of CTA 0 -- [0..63] compute warp 0, [64..127] the MMA thread
+#define FB_STAMP(slot) do { if (trace != nullptr && blockIdx.x == 0 && it == 1) trace[slot] = clock64(); } while (0)
   extern __shared__ uint8_t fb_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(fb_smem_raw) + 1023) & ~uintptr_t(1023));
+  if (smem + FB_SMEM_USED > fb_smem_raw + FB_SMEM) {  // never observed: the dynamic window starts 1024-byte aligned
+    if (threadIdx.x == 0) printf("tic: attention_bwd_fused: shared memory window is misaligned\n");
+    __trap();
+  }
   uint8_t* sQ = smem;
   uint8_t* sDO = sQ + FB_OPER_BYTES;
   uint8_t* sK = sDO + FB_OPER_BYTES;
   uint8_t* sV = sK + FB_OPER_BYTES;
   uint8_t* sStage = sV + FB_OPER_BYTES;  // [2 query tiles][2 chunks of 64 queries][128 key rows][128 B]
-  float* sL = reinterpret_cast<float*>(sStage + 2 * FB_STAGE_BYTES);  // [256] logsumexp * log2(e), +inf past N
+  uint8_t* sOut = sStage + 2 * FB_STAGE_BYTES;  // [8 warps][2][32 rows][64 B], 64-byte swizzle (TMA store sources)
+  float* sL = reinterpret_cast<float*>(sOut + FB_OUT_BYTES);  // [256] logsumexp * log2(e), +inf past N
   float* sD = sL + FB_ROWS;                                           // [256] delta = rowsum(dO o O)
   uint64_t* bars = reinterpret_cast<uint64_t*>(sD + FB_ROWS);
-  uint64_t* bar_load = bars + 0;  // [2] K + Q  |  V + dO + O
+  uint64_t* bar_load = bars + 0;  // [2] K + Q  |  dO + O + V
   uint64_t* bar_s = bars + 2;    // [2] score tiles of a block are in TMEM
   uint64_t* bar_p = bars + 4;    // [2] P^T / dS^T of a block written (8 warp arrivals)
   uint64_t* bar_acc = bars + 6;  // every MMA of a key tile has completed
@@ -90,7 +103,6 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
   uint8_t* sO = sStage + FB_STAGE_BYTES;  // O rows live in the second staging tile until delta has been computed
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int h = blockIdx.x, b = blockIdx.y;
   const int nkt = (N + 127) >> 7;             // key tiles of 128
   const int nqb = (N + 63) >> 6;              // query blocks of 64
   const int w_last = ((N - (nqb - 1) * 64) + 15) & ~15;  // width of the last query block (multiple of 16)
@@ -99,7 +111,7 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
   if (warp == 8) {
     if (lane == 0) {
       tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v); tma_prefetch_desc(&tm_do);
-      tma_prefetch_desc(&tm_o);
+      tma_prefetch_desc(&tm_o); tma_prefetch_desc(&tm_dq); tma_prefetch_desc(&tm_dk); tma_prefetch_desc(&tm_dv);
       mbar_init(&bar_load[0], 1);
       mbar_init(&bar_load[1], 1);
       mbar_init(&bar_s[0], 1);
@@ -108,75 +120,101 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       mbar_init(&bar_p[1], 8);
       mbar_init(bar_acc, 1);
       fence_mbar_init();
-      mbar_arrive_expect_tx(&bar_load[0], 2 * FB_OPER_BYTES);
-      tma_load_3d(sK, &tm_k, &bar_load[0], h * FB_HD, 0, b);
-      tma_load_3d(sQ, &tm_q, &bar_load[0], h * FB_HD, 0, b);
-      mbar_arrive_expect_tx(&bar_load[1], 3 * FB_OPER_BYTES);
-      tma_load_3d(sDO, &tm_do, &bar_load[1], h * FB_HD, 0, b);
-      tma_load_3d(sO, &tm_o, &bar_load[1], h * FB_HD, 0, b);
-      tma_load_3d(sV, &tm_v, &bar_load[1], h * FB_HD, 0, b);
     }
     __syncwarp();
     tmem_alloc(tmem_slot, 512);
   }
-  // per-query logsumexp (log2 domain); issued before the barrier so its latency overlaps the TMA loads
-  float L_mine = INFINITY;
-  if (threadIdx.x < N) L_mine = __ldg(lse + (static_cast<long long>(b) * H + h) * N + threadIdx.x) * FB_LOG2E;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // Persistent: this CTA walks the (image, head) items blockIdx.x, blockIdx.x + gridDim.x, ... The loads of item i+1
+  // are issued as soon as the last MMA of item i has completed, i.e. under the final accumulator drain of item i.
   if (warp == 8) {
     if (elect_one()) {  // one issuing thread on the uniform datapath (a lane == 0 test costs ~45 clk per MMA)
-      // ---------------------------------------------------------------------------------- MMA issue loop
+      // ---------------------------------------------------------------------------------- TMA + MMA issue loop
       constexpr uint32_t idesc_ts = make_idesc_bf16(128, FB_HD, false, true);
       constexpr uint32_t idesc_dq = make_idesc_bf16(128, FB_HD, true, true);
       const uint32_t aQ = smem_u32(sQ), aDO = smem_u32(sDO), aK = smem_u32(sK), aV = smem_u32(sV), aS = smem_u32(sStage);
-      auto issue_scores = [&](int j) {
-        const int kt = j >= nqb ? 1 : 0, qb = j - kt * nqb, buf = j & 1;
-        const int w = qb == nqb - 1 ? w_last : 64;
-        const uint32_t idesc = make_idesc_bf16(128, w, false, false);
-        const uint64_t dK_ = make_smem_desc_sw128(aK + kt * 16384, 0, 1024), dQ_ = make_smem_desc_sw128(aQ + qb * 8192, 0, 1024);
-        const uint64_t dV_ = make_smem_desc_sw128(aV + kt * 16384, 0, 1024), dO_ = make_smem_desc_sw128(aDO + qb * 8192, 0, 1024);
-        if (j == 0) { mbar_wait(&bar_load[0], 0); tc_fence_after(); }
-#pragma unroll
-        for (int k = 0; k < FB_HD / 16; ++k) umma_bf16_ss(tmem_base + buf * 64, dK_ + 2 * k, dQ_ + 2 * k, idesc, k > 0 ? 1u : 0u);
-        if (j == 0) { mbar_wait(&bar_load[1], 0); tc_fence_after(); }
-#pragma unroll
-        for (int k = 0; k < FB_HD / 16; ++k)
-          umma_bf16_ss(tmem_base + FB_COL_DP + buf * 64, dV_ + 2 * k, dO_ + 2 * k, idesc, k > 0 ? 1u : 0u);
-        umma_commit(&bar_s[buf]);
+      auto issue_loads = [&](int item) {
+        const int h = item % H, b = item / H;
+        mbar_arrive_expect_tx(&bar_load[0], 2 * FB_OPER_BYTES);
+        tma_load_3d(sK, &tm_k, &bar_load[0], h * FB_HD, 0, b);
+        tma_load_3d(sQ, &tm_q, &bar_load[0], h * FB_HD, 0, b);
+        mbar_arrive_expect_tx(&bar_load[1], 3 * FB_OPER_BYTES);
+        tma_load_3d(sDO, &tm_do, &bar_load[1], h * FB_HD, 0, b);
+        tma_load_3d(sO, &tm_o, &bar_load[1], h * FB_HD, 0, b);
+        tma_load_3d(sV, &tm_v, &bar_load[1], h * FB_HD, 0, b);
       };
-      issue_scores(0);
-      for (int j = 0; j < J; ++j) {
-        const int kt = j >= nqb ? 1 : 0, qb = j - kt * nqb, buf = j & 1;
-        if (j + 1 < J) issue_scores(j + 1);   // runs under the elementwise pass of block j
-        mbar_wait(&bar_p[buf], (j >> 1) & 1);
-        tc_fence_after();
-        const int ksteps = (qb == nqb - 1 ? w_last : 64) >> 4;
-        const uint64_t dO_mn = make_smem_desc_sw128(aDO + qb * 8192, 8192, 1024);
-        const uint64_t dQ_mn = make_smem_desc_sw128(aQ + qb * 8192, 8192, 1024);
-        for (int k = 0; k < ksteps; ++k) {  // dV += P^T dO
-          const uint32_t a = tmem_base + buf * 64 + (k >> 1) * 32 + (k & 1) * 8;
-          umma_bf16_ts(tmem_base + FB_COL_DV, a, dO_mn + 128 * k, idesc_ts, (qb > 0 || k > 0) ? 1u : 0u);
+      uint32_t ph_p = 0, use_acc = 0;  // ph_p: bit b = parity of the next completion of bar_p[b]
+      issue_loads(blockIdx.x);
+      for (int it = 0, item = blockIdx.x; item < num_items; ++it, item += gridDim.x) {
+        auto issue_scores = [&](int j) {
+          const int kt = j >= nqb ? 1 : 0, qb = j - kt * nqb, buf = j & 1;
+          const int w = qb == nqb - 1 ? w_last : 64;
+          const uint32_t idesc = make_idesc_bf16(128, w, false, false);
+          const uint64_t dK_ = make_smem_desc_sw128(aK + kt * 16384, 0, 1024), dQ_ = make_smem_desc_sw128(aQ + qb * 8192, 0, 1024);
+          const uint64_t dV_ = make_smem_desc_sw128(aV + kt * 16384, 0, 1024), dO_ = make_smem_desc_sw128(aDO + qb * 8192, 0, 1024);
+          if (j == 0) { mbar_wait(&bar_load[0], it & 1); tc_fence_after(); }
+#pragma unroll
+          for (int k = 0; k < FB_HD / 16; ++k) umma_bf16_ss(tmem_base + buf * 64, dK_ + 2 * k, dQ_ + 2 * k, idesc, k > 0 ? 1u : 0u);
+          if (j == 0) { mbar_wait(&bar_load[1], it & 1); tc_fence_after(); }
+#pragma unroll
+          for (int k = 0; k < FB_HD / 16; ++k)
+            umma_bf16_ss(tmem_base + FB_COL_DP + buf * 64, dV_ + 2 * k, dO_ + 2 * k, idesc, k > 0 ? 1u : 0u);
+          umma_commit(&bar_s[buf]);
+        };
+        FB_STAMP(64);
+        issue_scores(0);
+        FB_STAMP(65);
+        if (J > 1) issue_scores(1);
+        FB_STAMP(66);
+        for (int j = 0; j < J; ++j) {
+          const int kt = j >= nqb ? 1 : 0, qb = j - kt * nqb, buf = j & 1;
+          mbar_wait(&bar_p[buf], (ph_p >> buf) & 1);
+          FB_STAMP(70 + 2 * j);
+          ph_p ^= 1u << buf;
+          tc_fence_after();
+          const int ksteps = (qb == nqb - 1 ? w_last : 64) >> 4;
+          const uint64_t dO_mn = make_smem_desc_sw128(aDO + qb * 8192, 8192, 1024);
+          const uint64_t dQ_mn = make_smem_desc_sw128(aQ + qb * 8192, 8192, 1024);
+          for (int k = 0; k < ksteps; ++k) {  // dV += P^T dO
+            const uint32_t a = tmem_base + buf * 64 + (k >> 1) * 32 + (k & 1) * 8;
+            umma_bf16_ts(tmem_base + FB_COL_DV, a, dO_mn + 128 * k, idesc_ts, (qb > 0 || k > 0) ? 1u : 0u);
+          }
+          for (int k = 0; k < ksteps; ++k) {  // dK += dS^T Q
+            const uint32_t a = tmem_base + FB_COL_DP + buf * 64 + (k >> 1) * 32 + (k & 1) * 8;
+            umma_bf16_ts(tmem_base + FB_COL_DK, a, dQ_mn + 128 * k, idesc_ts, (qb > 0 || k > 0) ? 1u : 0u);
+          }
+          // the P^T / dS^T columns of this buffer have been consumed (in issue order): refill it with the scores of
+          // block j+2 before the dQ product, which the compute warps do not wait for
+          if (j + 2 < J) issue_scores(j + 2);
+          if ((qb & 1) || qb == nqb - 1) {    // dQ[query tile] += dS K over this key tile
+            const int qt = qb >> 1;
+            const int kvalid = min(128, N - kt * 128);
+            const int ks = (kvalid + 15) >> 4;
+            const uint64_t dS_mn = make_smem_desc_sw128(aS + qt * FB_STAGE_BYTES, 16384, 1024);
+            const uint64_t dK_mn = make_smem_desc_sw128(aK + kt * 16384, 8192, 1024);
+            for (int k = 0; k < ks; ++k)
+              umma_bf16_ss(tmem_base + FB_COL_DQ + qt * 64, dS_mn + 128 * k, dK_mn + 128 * k, idesc_dq, (kt > 0 || k > 0) ? 1u : 0u);
+          }
+          FB_STAMP(71 + 2 * j);
+          if (qb == nqb - 1) {
+            umma_commit(bar_acc);
+            if (kt == nkt - 1 && item + static_cast<int>(gridDim.x) < num_items) {
+              // every MMA of this item has read its operands: refill the operand buffers for the next item
+              mbar_wait(bar_acc, use_acc & 1);
+              FB_STAMP(100);
+              issue_loads(item + gridDim.x);
+              FB_STAMP(101);
+            }
+            ++use_acc;
+          }
         }
-        for (int k = 0; k < ksteps; ++k) {  // dK += dS^T Q
-          const uint32_t a = tmem_base + FB_COL_DP + buf * 64 + (k >> 1) * 32 + (k & 1) * 8;
-          umma_bf16_ts(tmem_base + FB_COL_DK, a, dQ_mn + 128 * k, idesc_ts, (qb > 0 || k > 0) ? 1u : 0u);
-        }
-        if ((qb & 1) || qb == nqb - 1) {    // dQ[query tile] += dS K over this key tile
-          const int qt = qb >> 1;
-          const int kvalid = min(128, N - kt * 128);
-          const int ks = (kvalid + 15) >> 4;
-          const uint64_t dS_mn = make_smem_desc_sw128(aS + qt * FB_STAGE_BYTES, 16384, 1024);
-          const uint64_t dK_mn = make_smem_desc_sw128(aK + kt * 16384, 8192, 1024);
-          for (int k = 0; k < ks; ++k)
-            umma_bf16_ss(tmem_base + FB_COL_DQ + qt * 64, dS_mn + 128 * k, dK_mn + 128 * k, idesc_dq, (kt > 0 || k > 0) ? 1u : 0u);
-        }
-        if (qb == nqb - 1) umma_commit(bar_acc);
       }
     }
+    __syncwarp();
   } else {
     // ------------------------------------------------------------------------------------ compute warps
     const int quad = warp & 3, half = warp >> 2;
@@ -185,146 +223,173 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     const int r = quad * 32 + lane;  // row within the 128-row tile
     const uint32_t stage_row = smem_u32(sStage) + r * 128;
     const int sw = r & 7;
+    const int t = threadIdx.x;       // 0..255: the query whose delta / logsumexp this thread prepares
     const uint32_t aL = smem_u32(sL), aD = smem_u32(sD);
-    {
-      // delta[q] = sum_d dO[q, d] * O[q, d], one query row per thread, both rows read from swizzled shared memory
-      const int t = threadIdx.x;
-      mbar_wait(&bar_load[1], 0);
-      const uint32_t ro = smem_u32(sO) + t * 128, rd = smem_u32(sDO) + t * 128;
-      float dsum = 0.f;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const uint32_t off = static_cast<uint32_t>((i ^ (t & 7)) << 4);
-        const uint4 a = ld_shared_v4(ro + off), g = ld_shared_v4(rd + off);
-        dsum = fmaf(bf16_lo(a.x), bf16_lo(g.x), dsum); dsum = fmaf(bf16_hi(a.x), bf16_hi(g.x), dsum);
-        dsum = fmaf(bf16_lo(a.y), bf16_lo(g.y), dsum); dsum = fmaf(bf16_hi(a.y), bf16_hi(g.y), dsum);
-        dsum = fmaf(bf16_lo(a.z), bf16_lo(g.z), dsum); dsum = fmaf(bf16_hi(a.z), bf16_hi(g.z), dsum);
-        dsum = fmaf(bf16_lo(a.w), bf16_lo(g.w), dsum); dsum = fmaf(bf16_hi(a.w), bf16_hi(g.w), dsum);
-      }
-      sL[t] = L_mine;  // +inf for padded queries: exp2(-inf) = 0
-      sD[t] = dsum;    // rows past N are zero-filled by TMA: delta = 0
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-    }
-    int pending_kt = -1;  // key tile whose dV / dK still have to be drained
-    auto drain_kt = [&](int kt) {
-      const bool quad_active = kt * 128 + quad * 32 < N;
-      mbar_wait(bar_acc, kt & 1);
-      tc_fence_after();
-      const int row = kt * 128 + r;
-      const long long tok = static_cast<long long>(b) * N + row;
-#pragma unroll 1
-      for (int a = 0; a < 2; ++a) {  // a = 0: dV (unscaled), a = 1: dK (* scale)
-        if (!quad_active) break;
-        const float f = a == 0 ? 1.0f : scale;
-        uint32_t rr[32];
-        tmem_ld_32x32b_x32(lane_addr + (a == 0 ? FB_COL_DV : FB_COL_DK) + half * 32, rr);
-        tmem_ld_wait();
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(__uint_as_float(rr[2 * i]) * f, __uint_as_float(rr[2 * i + 1]) * f);
-        if (row < N) {
-          uint4* dst = reinterpret_cast<uint4*>((a == 0 ? dv : dk) + tok * ldg + h * FB_HD + half * 32);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) dst[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
-        }
-        if (bias_grad != nullptr) {  // column sums of the bf16 gradient rows = bias gradient of the fused QKV Linear
-          float v[32];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            v[2 * i] = row < N ? bf16_lo(pk[i]) : 0.f;
-            v[2 * i + 1] = row < N ? bf16_hi(pk[i]) : 0.f;
-          }
-          const float cs = warp_colsum32(v, lane);
-          atomicAdd(bias_grad + (a == 0 ? 2 : 1) * H * FB_HD + h * FB_HD + half * 32 + lane, cs);
-        }
-      }
-      tc_fence_before();
+    const uint32_t out_tile = smem_u32(sOut) + warp * 4096;
+    uint32_t out_sel = 0;
+    const uint32_t ro = smem_u32(sO) + t * 128, rd = smem_u32(sDO) + t * 128;
+    uint32_t ph_s = 0, use_acc = 0;  // ph_s: bit b = parity of the next completion of bar_s[b]
+    auto load_lse = [&](int item) -> float {  // per-query logsumexp, +inf past N: exp2(-inf) = 0
+      return (item < num_items && t < N) ? __ldg(lse + static_cast<long long>(item) * N + t) : INFINITY;
     };
-    for (int j = 0; j < J; ++j) {
-      const int kt = j >= nqb ? 1 : 0, qb = j - kt * nqb, buf = j & 1;
-      const int w = qb == nqb - 1 ? w_last : 64;
-      const bool quad_active = kt * 128 + quad * 32 < N;
-      const bool row_valid = kt * 128 + r < N;
-      mbar_wait(&bar_s[buf], (j >> 1) & 1);
-      tc_fence_after();
-      if (quad_active && half * 32 < w) {
-        uint32_t s[32], dp[32];
-        tmem_ld_32x32b_x32(lane_addr + buf * 64 + half * 32, s);
-        tmem_ld_32x32b_x32(lane_addr + FB_COL_DP + buf * 64 + half * 32, dp);
-        tmem_ld_wait();
-        const uint32_t L4 = aL + (qb * 64 + half * 32) * 4, D4 = aD + (qb * 64 + half * 32) * 4;
-        uint32_t pw[16], dw[16];
+    float L_next = load_lse(blockIdx.x);
+    for (int it = 0, item = blockIdx.x; item < num_items; ++it, item += gridDim.x) {
+      const int h = item % H, b = item / H;
+#define FB_CSTAMP(slot) do { if (threadIdx.x == 0) FB_STAMP(slot); } while (0)
+      FB_CSTAMP(0);
+      {
+        // delta[q] = sum_d dO[q, d] * O[q, d], one query row per thread, both rows read from swizzled shared memory
+        mbar_wait(&bar_load[1], it & 1);
+        FB_CSTAMP(1);
+        float dsum = 0.f;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float4 Lq = ld_shared_f4(L4 + 16 * i), Dq = ld_shared_f4(D4 + 16 * i);
-          const float p0 = ex2_approx(fmaf(__uint_as_float(s[4 * i + 0]), c2, -Lq.x));
-          const float p1 = ex2_approx(fmaf(__uint_as_float(s[4 * i + 1]), c2, -Lq.y));
-          const float p2 = ex2_approx(fmaf(__uint_as_float(s[4 * i + 2]), c2, -Lq.z));
-          const float p3 = ex2_approx(fmaf(__uint_as_float(s[4 * i + 3]), c2, -Lq.w));
-          pw[2 * i] = pack_bf16x2(p0, p1);
-          pw[2 * i + 1] = pack_bf16x2(p2, p3);
-          dw[2 * i] = pack_bf16x2(p0 * (__uint_as_float(dp[4 * i + 0]) - Dq.x), p1 * (__uint_as_float(dp[4 * i + 1]) - Dq.y));
-          dw[2 * i + 1] = pack_bf16x2(p2 * (__uint_as_float(dp[4 * i + 2]) - Dq.z), p3 * (__uint_as_float(dp[4 * i + 3]) - Dq.w));
+          const uint32_t off = static_cast<uint32_t>((i ^ (t & 7)) << 4);
+          const uint4 a = ld_shared_v4(ro + off), g = ld_shared_v4(rd + off);
+          dsum = fmaf(bf16_lo(a.x), bf16_lo(g.x), dsum); dsum = fmaf(bf16_hi(a.x), bf16_hi(g.x), dsum);
+          dsum = fmaf(bf16_lo(a.y), bf16_lo(g.y), dsum); dsum = fmaf(bf16_hi(a.y), bf16_hi(g.y), dsum);
+          dsum = fmaf(bf16_lo(a.z), bf16_lo(g.z), dsum); dsum = fmaf(bf16_hi(a.z), bf16_hi(g.z), dsum);
+          dsum = fmaf(bf16_lo(a.w), bf16_lo(g.w), dsum); dsum = fmaf(bf16_hi(a.w), bf16_hi(g.w), dsum);
         }
-        tmem_st_32x32b_x16(lane_addr + buf * 64 + half * 32, pw);
-        tmem_st_32x32b_x16(lane_addr + FB_COL_DP + buf * 64 + half * 32, dw);
-        // dS^T row -> staging tile of this query tile (chunk = 64-query block), zero for key rows past N so that the
-        // dQ product never sees a non-finite value against the zero-filled K rows
-        const uint32_t dst = stage_row + (qb >> 1) * FB_STAGE_BYTES + (qb & 1) * 16384;
+        sL[t] = L_next * FB_LOG2E;  // log2 domain (L_next was loaded under the previous item's final drain)
+        sD[t] = dsum;    // rows past N are zero-filled by TMA: delta = 0
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        FB_CSTAMP(2);
+      }
+      auto colsum_to = [&](const uint32_t (&pk)[16], bool valid, float* dst) {
+        float v[32];
 #pragma unroll
-        for (int pc = 0; pc < 4; ++pc) {
-          const uint32_t a = dst + (((half * 4 + pc) ^ sw) << 4);
-          if (row_valid) st_shared_v4(a, dw[4 * pc], dw[4 * pc + 1], dw[4 * pc + 2], dw[4 * pc + 3]);
-          else st_shared_v4(a, 0u, 0u, 0u, 0u);
+        for (int i = 0; i < 16; ++i) {
+          v[2 * i] = valid ? bf16_lo(pk[i]) : 0.f;
+          v[2 * i + 1] = valid ? bf16_hi(pk[i]) : 0.f;
         }
-        tmem_st_wait();
+        const float cs = warp_colsum32(v, lane);
+        atomicAdd(dst + h * FB_HD + half * 32 + lane, cs);
+      };
+      // This warp's 32 x 32 bf16 output tile -> one of its two private staging tiles -> one TMA store (rows past N are
+      // clipped by the tensor map). Direct 16-byte stores at a 6 KB row pitch cost ~300 clk per instruction and stalled
+      // the drain.
+      auto store_tile = [&](const CUtensorMap* tm, const uint32_t (&pk)[16], int row0) {
+        if (lane == 0) tma_store_wait_read<1>();  // the store before the previous one has finished reading this tile
+        __syncwarp();
+        out_sel ^= 1u;
+        const uint32_t region = out_tile + out_sel * 2048;
+        const uint32_t base = region + lane * 64;
+        const int x = (lane >> 1) & 3;
+#pragma unroll
+        for (int pc = 0; pc < 4; ++pc)
+          st_shared_v4(base + ((pc ^ x) << 4), pk[4 * pc], pk[4 * pc + 1], pk[4 * pc + 2], pk[4 * pc + 3]);
         fence_proxy_async();
-      }
-      if (pending_kt >= 0) {  // the previous key tile's accumulators must be read before this block's TS MMAs overwrite them
-        drain_kt(pending_kt);
-        pending_kt = -1;
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_p[buf]);
-
-      if (qb == nqb - 1) {
-        if (kt < nkt - 1) {
-          pending_kt = kt;  // drained after the next block's elementwise pass
-        } else {
-          drain_kt(kt);
-          tc_fence_after();
-          for (int qt = 0; qt < nkt; ++qt) {
-            const int qrow = qt * 128 + r;
-            if (qt * 128 + quad * 32 >= N) break;
-            uint32_t rr[32];
-            tmem_ld_32x32b_x32(lane_addr + FB_COL_DQ + qt * 64 + half * 32, rr);
-            tmem_ld_wait();
-            uint32_t pk[16];
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_3d_addr(tm, region, h * FB_HD + half * 32, row0, b);
+          tma_store_commit();
+        }
+      };
+      int pending_kt = -1;  // key tile whose dV / dK still have to be drained
+      auto drain_kt = [&](int kt) {
+        const bool quad_active = kt * 128 + quad * 32 < N;
+        mbar_wait(bar_acc, use_acc & 1);
+        ++use_acc;
+        tc_fence_after();
+        const int row = kt * 128 + r;
+#pragma unroll 1
+        for (int a = 0; a < 2; ++a) {  // a = 0: dV (unscaled), a = 1: dK (* scale)
+          if (!quad_active) break;
+          const float f = a == 0 ? 1.0f : scale;
+          uint32_t rr[32];
+          tmem_ld_32x32b_x32(lane_addr + (a == 0 ? FB_COL_DV : FB_COL_DK) + half * 32, rr);
+          tmem_ld_wait();
+          uint32_t pk[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i)
-              pk[i] = pack_bf16x2(__uint_as_float(rr[2 * i]) * scale, __uint_as_float(rr[2 * i + 1]) * scale);
-            if (qrow < N) {
-              uint4* dst = reinterpret_cast<uint4*>(dq + (static_cast<long long>(b) * N + qrow) * ldg + h * FB_HD + half * 32);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) dst[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
-            }
-            if (bias_grad != nullptr) {
-              float v[32];
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                v[2 * i] = qrow < N ? bf16_lo(pk[i]) : 0.f;
-                v[2 * i + 1] = qrow < N ? bf16_hi(pk[i]) : 0.f;
-              }
-              const float cs = warp_colsum32(v, lane);
-              atomicAdd(bias_grad + h * FB_HD + half * 32 + lane, cs);
-            }
-          }
+          for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(__uint_as_float(rr[2 * i]) * f, __uint_as_float(rr[2 * i + 1]) * f);
+          store_tile(a == 0 ? &tm_dv : &tm_dk, pk, kt * 128 + quad * 32);
+          // column sums of the bf16 gradient rows = bias gradient of the fused QKV Linear (k: bit 1, v: bit 2)
+          if (bias_mask & (a == 0 ? 4 : 2)) colsum_to(pk, row < N, bias_grad + (a == 0 ? 2 : 1) * H * FB_HD);
         }
         tc_fence_before();
+      };
+      for (int j = 0; j < J; ++j) {
+        const int kt = j >= nqb ? 1 : 0, qb = j - kt * nqb, buf = j & 1;
+        const int w = qb == nqb - 1 ? w_last : 64;
+        const bool quad_active = kt * 128 + quad * 32 < N;
+        const bool row_valid = kt * 128 + r < N;
+        mbar_wait(&bar_s[buf], (ph_s >> buf) & 1);
+        FB_CSTAMP(4 + 3 * j);
+        ph_s ^= 1u << buf;
+        tc_fence_after();
+        if (quad_active && half * 32 < w) {
+          uint32_t s[32], dp[32];
+          tmem_ld_32x32b_x32(lane_addr + buf * 64 + half * 32, s);
+          tmem_ld_32x32b_x32(lane_addr + FB_COL_DP + buf * 64 + half * 32, dp);
+          tmem_ld_wait();
+          const uint32_t L4 = aL + (qb * 64 + half * 32) * 4, D4 = aD + (qb * 64 + half * 32) * 4;
+          uint32_t pw[16], dw[16];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 Lq = ld_shared_f4(L4 + 16 * i), Dq = ld_shared_f4(D4 + 16 * i);
+            const float p0 = ex2_approx(fmaf(__uint_as_float(s[4 * i + 0]), c2, -Lq.x));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(s[4 * i + 1]), c2, -Lq.y));
+            const float p2 = ex2_approx(fmaf(__uint_as_float(s[4 * i + 2]), c2, -Lq.z));
+            const float p3 = ex2_approx(fmaf(__uint_as_float(s[4 * i + 3]), c2, -Lq.w));
+            pw[2 * i] = pack_bf16x2(p0, p1);
+            pw[2 * i + 1] = pack_bf16x2(p2, p3);
+            dw[2 * i] = pack_bf16x2(p0 * (__uint_as_float(dp[4 * i + 0]) - Dq.x), p1 * (__uint_as_float(dp[4 * i + 1]) - Dq.y));
+            dw[2 * i + 1] = pack_bf16x2(p2 * (__uint_as_float(dp[4 * i + 2]) - Dq.z), p3 * (__uint_as_float(dp[4 * i + 3]) - Dq.w));
+          }
+          tmem_st_32x32b_x16(lane_addr + buf * 64 + half * 32, pw);
+          tmem_st_32x32b_x16(lane_addr + FB_COL_DP + buf * 64 + half * 32, dw);
+          // dS^T row -> staging tile of this query tile (chunk = 64-query block), zero for key rows past N so that the
+          // dQ product never sees a non-finite value against the zero-filled K rows
+          const uint32_t dst = stage_row + (qb >> 1) * FB_STAGE_BYTES + (qb & 1) * 16384;
+#pragma unroll
+          for (int pc = 0; pc < 4; ++pc) {
+            const uint32_t a = dst + (((half * 4 + pc) ^ sw) << 4);
+            if (row_valid) st_shared_v4(a, dw[4 * pc], dw[4 * pc + 1], dw[4 * pc + 2], dw[4 * pc + 3]);
+            else st_shared_v4(a, 0u, 0u, 0u, 0u);
+          }
+          tmem_st_wait();
+          fence_proxy_async();
+        }
+        FB_CSTAMP(5 + 3 * j);
+        if (pending_kt >= 0) {  // the previous key tile's accumulators must be read before this block's TS MMAs overwrite them
+          drain_kt(pending_kt);
+          pending_kt = -1;
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_p[buf]);
+        FB_CSTAMP(6 + 3 * j);
+
+        if (qb == nqb - 1) {
+          if (kt < nkt - 1) {
+            pending_kt = kt;  // drained after the next block's elementwise pass
+          } else {
+            L_next = load_lse(item + gridDim.x);  // in flight during the final drain
+            drain_kt(kt);
+            FB_CSTAMP(40);
+            tc_fence_after();
+            for (int qt = 0; qt < nkt; ++qt) {
+              const int qrow = qt * 128 + r;
+              if (qt * 128 + quad * 32 >= N) break;
+              uint32_t rr[32];
+              tmem_ld_32x32b_x32(lane_addr + FB_COL_DQ + qt * 64 + half * 32, rr);
+              tmem_ld_wait();
+              uint32_t pk[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                pk[i] = pack_bf16x2(__uint_as_float(rr[2 * i]) * scale, __uint_as_float(rr[2 * i + 1]) * scale);
+              store_tile(&tm_dq, pk, qt * 128 + quad * 32);
+              if (bias_mask & 1) colsum_to(pk, qrow < N, bias_grad);
+            }
+            FB_CSTAMP(41);
+            tc_fence_before();
+          }
+        }
       }
     }
   }
+  if (warp < 8 && lane == 0) tma_store_wait_read<0>();  // the staging tiles must outlive the last TMA stores
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -334,12 +399,12 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
 }  // namespace
 
 // q/k/v: [B*N, ...] pitch ld, head h at column h*64; o / dout: [B*N, H*64]; dq/dk/dv pitch ldg. bias_grad (optional):
-// fp32 [3*H*64] laid out q | k | v, ACCUMULATES the column sums of dq / dk / dv (the fused QKV bias gradient).
+// fp32 [3*H*64] laid out q | k | v, ACCUMULATES the column sums of dq (bias_mask bit 0) / dk (bit 1) / dv (bit 2).
 int attention_bwd_fused(const void* q, const void* k, const void* v, long long ld, const void* o, long long ldo,
                         const void* dout, long long lddo, const float* lse, void* dq, void* dk, void* dv, long long ldg,
-                        float* bias_grad, int B, int N, int H, float scale, cudaStream_t stream) {
+                        float* bias_grad, int bias_mask, int B, int N, int H, float scale, cudaStream_t stream) {
   if (N > FB_ROWS) return set_error(kErrUnsupported, "attention_bwd_fused: N=%d > %d", N, FB_ROWS);
-  CUtensorMap tq, tk, tv, tdo, to;
+  CUtensorMap tq, tk, tv, tdo, to, tdq, tdk, tdv;
   const uint64_t D = static_cast<uint64_t>(H) * FB_HD;
   int rc = encode_tmap_3d_bf16(&tq, q, D, N, B, ld, static_cast<uint64_t>(N) * ld, 64, FB_ROWS);
   if (rc) return rc;
@@ -351,16 +416,47 @@ int attention_bwd_fused(const void* q, const void* k, const void* v, long long l
   if (rc) return rc;
   rc = encode_tmap_3d_bf16(&to, o, D, N, B, ldo, static_cast<uint64_t>(N) * ldo, 64, FB_ROWS);
   if (rc) return rc;
+  // outputs: 32-column x 32-row boxes (one compute warp's tile), 64-byte swizzle
+  rc = encode_tmap_3d_bf16_sw(&tdq, dq, D, N, B, ldg, static_cast<uint64_t>(N) * ldg, 32, 32, 64);
+  if (rc) return rc;
+  rc = encode_tmap_3d_bf16_sw(&tdk, dk, D, N, B, ldg, static_cast<uint64_t>(N) * ldg, 32, 32, 64);
+  if (rc) return rc;
+  rc = encode_tmap_3d_bf16_sw(&tdv, dv, D, N, B, ldg, static_cast<uint64_t>(N) * ldg, 32, 32, 64);
+  if (rc) return rc;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(attn_bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM);
     if (e != cudaSuccess) return set_error(kErrCuda, "attention_bwd_fused: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  dim3 grid(H, B);
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (num_sms <= 0) num_sms = 148;
+  }
+  const int items = B * H;
+  if (bias_grad == nullptr) bias_mask = 0;
+  dim3 grid(items < num_sms ? items : num_sms);  // persistent: one CTA per SM walks the (image, head) items
+  long long* trace = nullptr;
+  static const bool want_trace = getenv("TIC_FB_TRACE") != nullptr;  // dev tool: per-phase clock stamps of CTA 0
+  if (want_trace) {
+    cudaMallocManaged(&trace, 128 * sizeof(long long));
+    for (int i = 0; i < 128; ++i) trace[i] = 0;
+  }
   attn_bwd_fused_kernel<<<grid, FB_THREADS, FB_SMEM, stream>>>(
-      tq, tk, tv, tdo, to, lse, reinterpret_cast<__nv_bfloat16*>(dq), reinterpret_cast<__nv_bfloat16*>(dk), reinterpret_cast<__nv_bfloat16*>(dv), ldg,
-      bias_grad, N, H, scale);
+      tq, tk, tv, tdo, to, tdq, tdk, tdv, lse, bias_grad, bias_mask, N, H, items, scale, trace);
+  if (trace != nullptr) {
+    cudaDeviceSynchronize();
+    const long long t0 = trace[0];
+    fprintf(stderr, "[fb trace] compute warp 0 (clk since item start):");
+    for (int i = 0; i < 64; ++i) if (trace[i]) fprintf(stderr, " c%d=%lld", i, trace[i] - t0);
+    fprintf(stderr, "\n[fb trace] mma thread:");
+    for (int i = 64; i < 128; ++i) if (trace[i]) fprintf(stderr, " m%d=%lld", i - 64, trace[i] - t0);
+    fprintf(stderr, "\n");
+    cudaFree(trace);
+  }
   return check_launch("attention_bwd_fused");
 }
 

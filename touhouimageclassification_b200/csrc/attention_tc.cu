@@ -488,14 +488,14 @@ int attention_fwd_tc(const void* q, const void* k, const void* v, long long ld, 
 int attention_bwd_tc(const void* q, const void* k, const void* v, long long ld, const void* o, long long ldo,
                      const void* dout, long long lddo, const float* lse, float* delta, void* dq, void* dk, void* dv,
                      long long lddqkv, int B, int N, int H, int head_dim, float scale, cudaStream_t stream,
-                     float* bias_grad) {
+                     float* bias_grad, int bias_mask) {
   if (head_dim != AT_HD) return set_error(kErrUnsupported, "attention: head_dim=%d (only 64 is supported)", head_dim);
   if (B <= 0 || N <= 0) return kOk;
   if ((ld % 8) || (lddo % 8) || (lddqkv % 8) || (ldo % 8))
     return set_error(kErrInvalidArg, "attention_bwd: pitches must be multiples of 8");
   if (N <= 256) {  // whole head in shared memory: one fused kernel (delta, dQ, dK, dV, QKV bias gradient)
     ProfScope prof("attention_bwd", 10.0 * B * H * static_cast<double>(N) * N * AT_HD, 16.0 * B * H * static_cast<double>(N) * AT_HD, stream);
-    return attention_bwd_fused(q, k, v, ld, o, ldo, dout, lddo, lse, dq, dk, dv, lddqkv, bias_grad, B, N, H, scale, stream);
+    return attention_bwd_fused(q, k, v, ld, o, ldo, dout, lddo, lse, dq, dk, dv, lddqkv, bias_grad, bias_mask, B, N, H, scale, stream);
   }
   ProfScope prof("attention_bwd", 10.0 * B * H * static_cast<double>(N) * N * AT_HD, 16.0 * B * H * static_cast<double>(N) * AT_HD, stream);
   int rc = attention_delta(o, ldo, dout, lddo, delta, B, N, H, stream);
@@ -507,11 +507,12 @@ int attention_bwd_tc(const void* q, const void* k, const void* v, long long ld, 
   rc = launch_bwd<true>(k, v, ld, ld, q, dout, ld, lddo, lse, delta, dk, dv, lddqkv, B, N, H, scale, stream);
   if (rc || bias_grad == nullptr) return rc;
   const int Dm = H * AT_HD;
-  rc = colsum_bf16(dq, lddqkv, B * N, Dm, bias_grad, stream);
+  if (bias_mask & 1) rc = colsum_bf16(dq, lddqkv, B * N, Dm, bias_grad, stream);
   if (rc) return rc;
-  rc = colsum_bf16(dk, lddqkv, B * N, Dm, bias_grad + Dm, stream);
+  if (bias_mask & 2) rc = colsum_bf16(dk, lddqkv, B * N, Dm, bias_grad + Dm, stream);
   if (rc) return rc;
-  return colsum_bf16(dv, lddqkv, B * N, Dm, bias_grad + 2 * Dm, stream);
+  if (bias_mask & 4) rc = colsum_bf16(dv, lddqkv, B * N, Dm, bias_grad + 2 * Dm, stream);
+  return rc;
 }
 
 }  // namespace tic

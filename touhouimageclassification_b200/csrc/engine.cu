@@ -300,13 +300,18 @@ int vit_backward(const tic_vit_config* c, const float* P32, const void* P16v, in
       TIC_TRY(layernorm_bwd(dh, D, xmid, D, mean2, rstd2, p32 + L.ln2_w, dx, D, M, D, dx, D, dxb, D, g + L.ln2_w,
                             g + L.ln2_b, g + L.o_b, st));  // + out-proj bias grad = colsum(dxb)
       // attention output projection: xmid = x_in + ctx Wo^T + bo
+      // dctx = dxb Wo; its column sums are the VALUE bias gradient: sum_k dV[k,:] = sum_q (sum_k P[q,k]) dO[q,:] = sum_q dO[q,:]
+      // because every softmax row sums to one -- accumulated for free in this GEMM's epilogue.
       TIC_TRY(gemm_bf16(dxb, D, false, p16 + L.o_w, D, true, M, D, D, kEpiBf16, dctx, D, nullptr, 0, nullptr, nullptr, 0,
-                        0, 1, st));
+                        0, 1, st, g + L.qkv_b + 2 * D));
       TIC_TRY(gemm_bf16(dxb, D, true, ctx, D, true, D, D, M, kEpiF32Atomic, g + L.o_w, D, nullptr, 0, nullptr, nullptr, 0,
                         0, pick_splits(D, D, M), st));
       // attention core
       TIC_TRY(attention_bwd_tc(qkv, qkv + D, qkv + 2 * D, 3 * D, ctx, D, dctx, D, lse, delta, dqkv, dqkv + D, dqkv + 2 * D,
-                            3 * D, B, N, H, 64, scale, st, g + L.qkv_b));  // + QKV bias gradient = colsum(dqkv)
+                            3 * D, B, N, H, 64, scale, st, g + L.qkv_b, 1));
+      // bias gradients of the fused QKV Linear: query = colsum(dq), accumulated by the attention backward (mask 1);
+      // value = colsum(dctx), above; key = exactly 0 (sum_k dS[q,k] = 0: softmax is invariant to a shift of all keys,
+      // SURVEY Appendix D.3 -- the reference computes ~1e-10 of rounding noise here), so it is left untouched.
       // fused QKV projection
       TIC_TRY(gemm_bf16(dqkv, 3 * D, false, p16 + L.qkv_w, D, true, M, D, 3 * D, kEpiBf16, dh, D, nullptr, 0, nullptr,
                         nullptr, 0, 0, 1, st));

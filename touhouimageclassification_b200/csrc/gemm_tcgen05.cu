@@ -60,7 +60,7 @@ struct GemmParams {
   const void* aux;
   long long ldaux;
   int aux_int;  // kEpiF32PosEmbed: patches per image (P)
-  float* colsum;  // kEpiBf16DGelu: optional, accumulates column sums of the bf16 output (bias gradient)
+  float* colsum;  // kEpiBf16 / kEpiBf16DGelu: optional, accumulates column sums of the bf16 output (a bias gradient)
   int exact;      // fp32 verification mode: kEpiF32Resid / kEpiF32PosEmbed add without the bf16 rounding of autocast
 };
 
@@ -284,7 +284,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             a.x += bias.x; a.y += bias.y; a.z += bias.z; a.w += bias.w;
             if constexpr (EPI == kEpiBf16) {
               __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<long long>(row) * p.ldo + col;
-              *reinterpret_cast<uint2*>(o) = make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
+              const uint2 w = make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
+              *reinterpret_cast<uint2*>(o) = w;
+              if (p.colsum != nullptr) { csum.x += bf16_lo(w.x); csum.y += bf16_hi(w.x); csum.z += bf16_lo(w.y); csum.w += bf16_hi(w.y); }
             } else if constexpr (EPI == kEpiBf16Gelu) {
               // The reference evaluates GELU on the bf16-rounded fc1 output (autocast).
               const uint32_t p0 = pack_bf16x2(a.x, a.y), p1 = pack_bf16x2(a.z, a.w);
@@ -326,7 +328,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                   make_float4(a.x + x.x, a.y + x.y, a.z + x.z, a.w + x.w);
             }
           }
-          if constexpr (EPI == kEpiBf16DGelu) {
+          if constexpr (EPI == kEpiBf16DGelu || EPI == kEpiBf16) {
             if (p.colsum != nullptr) {  // lanes with the same 4-column group (lane & 7) hold partial sums over 8 rows each
 #pragma unroll
               for (int o = 8; o < 32; o <<= 1) {

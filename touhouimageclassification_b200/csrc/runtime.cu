@@ -127,14 +127,23 @@ int encode_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t dim0, uint6
 // 3D bf16 tensor map, 128B swizzle: [dim2][dim1][dim0] with dim0 contiguous; box = box0 x box1 x 1.
 int encode_tmap_3d_bf16(CUtensorMap* out, const void* base, uint64_t dim0, uint64_t dim1, uint64_t dim2,
                         uint64_t pitch1_elems, uint64_t pitch2_elems, uint32_t box0, uint32_t box1) {
+  return encode_tmap_3d_bf16_sw(out, base, dim0, dim1, dim2, pitch1_elems, pitch2_elems, box0, box1, 128);
+}
+
+// Same with a selectable swizzle span in bytes (0 = none, 32, 64, 128); box0 * 2 bytes must not exceed the span.
+int encode_tmap_3d_bf16_sw(CUtensorMap* out, const void* base, uint64_t dim0, uint64_t dim1, uint64_t dim2,
+                           uint64_t pitch1_elems, uint64_t pitch2_elems, uint32_t box0, uint32_t box1, int swizzle_bytes) {
   std::call_once(g_encode_once, load_encode);
   if (g_encode == nullptr) return set_error(kErrCuda, "cuTensorMapEncodeTiled is not available from the driver");
   cuuint64_t dims[3] = {dim0, dim1, dim2};
   cuuint64_t strides[2] = {pitch1_elems * 2, pitch2_elems * 2};
   cuuint32_t box[3] = {box0, box1, 1};
   cuuint32_t estr[3] = {1, 1, 1};
+  const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                               : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                               : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
   CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return set_error(kErrCuda, "cuTensorMapEncodeTiled(3d) failed (%d) base=%p dims=%llu,%llu,%llu box=%u,%u", (int)r, base,

@@ -170,6 +170,18 @@ TIC_DEVINL void tma_store_2d(const void* desc, const void* smem_src, int32_t c0,
                : "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
                : "memory");
 }
+TIC_DEVINL void tma_store_3d(const void* desc, const void* smem_src, int32_t c0, int32_t c1, int32_t c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               :
+               : "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+TIC_DEVINL void tma_store_3d_addr(const void* desc, uint32_t smem_addr, int32_t c0, int32_t c1, int32_t c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               :
+               : "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_addr), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 TIC_DEVINL void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 TIC_DEVINL void tma_store_wait_read() {
@@ -355,5 +367,8 @@ int encode_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t dim0, uint6
 
 int encode_tmap_3d_bf16(CUtensorMap* out, const void* base, uint64_t dim0, uint64_t dim1, uint64_t dim2,
                         uint64_t pitch1_elems, uint64_t pitch2_elems, uint32_t box0, uint32_t box1);
+
+int encode_tmap_3d_bf16_sw(CUtensorMap* out, const void* base, uint64_t dim0, uint64_t dim1, uint64_t dim2,
+                           uint64_t pitch1_elems, uint64_t pitch2_elems, uint32_t box0, uint32_t box1, int swizzle_bytes);
 
 }  // namespace tic

@@ -88,11 +88,11 @@ int attention_fwd_tc(const void* q, const void* k, const void* v, long long ld, 
 int attention_bwd_tc(const void* q, const void* k, const void* v, long long ld, const void* o, long long ldo,
                      const void* dout, long long lddo, const float* lse, float* delta, void* dq, void* dk, void* dv,
                      long long lddqkv, int B, int N, int H, int head_dim, float scale, cudaStream_t stream,
-                     float* bias_grad = nullptr);
+                     float* bias_grad = nullptr, int bias_mask = 7);
 // attention_bwd_fused.cu
 int attention_bwd_fused(const void* q, const void* k, const void* v, long long ld, const void* o, long long ldo,
                         const void* dout, long long lddo, const float* lse, void* dq, void* dk, void* dv, long long ldg,
-                        float* bias_grad, int B, int N, int H, float scale, cudaStream_t stream);
+                        float* bias_grad, int bias_mask, int B, int N, int H, float scale, cudaStream_t stream);
 int attention_delta(const void* o, long long ldo, const void* dout, long long lddo, float* delta, int B, int N, int H,
                     cudaStream_t stream);
 
