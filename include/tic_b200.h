@@ -49,9 +49,10 @@ TIC_API int64_t tic_prof_collect(char* buf_host, int64_t buflen);
  *   b_mn_major = 0: B is [N,K] row-major (pitch ldb);  1: B is stored [K,N] row-major (pitch ldb).
  * epilogue:
  *   0 TIC_EPI_BF16        out(bf16)  = acc + bias
- *   1 TIC_EPI_BF16_GELU   out2(bf16) = pre = bf16(acc + bias); out(bf16) = gelu_erf(pre)
+ *   1 TIC_EPI_BF16_GELU   pre = bf16(acc + bias); out(bf16) = gelu_erf(pre); out2(bf16, optional) = gelu_erf'(pre),
+ *                         the only thing the backward of this layer needs from the forward
  *   2 TIC_EPI_F32_RESID   out(f32)   = bf16(acc + bias) + aux(f32)[m,n]        (residual stream)
- *   3 TIC_EPI_BF16_DGELU  out(bf16)  = bf16(acc) * gelu_erf'(aux(bf16)[m,n])   (fc2 dgrad)
+ *   3 TIC_EPI_BF16_DGELU  out(bf16)  = bf16(acc) * aux(bf16)[m,n], aux = out2 of TIC_EPI_BF16_GELU   (fc2 dgrad)
  *   4 TIC_EPI_F32         out(f32)   = acc + bias
  *   5 TIC_EPI_F32_ATOMIC  out(f32)  += acc   (split-K partial sums; `splits` > 1 allowed)
  *   6 TIC_EPI_F32_POSEMB  patch embedding: row m = img * P + p is written to out row

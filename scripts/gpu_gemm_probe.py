@@ -45,10 +45,12 @@ def case_nt(M, N, K, splits):  # wgrad: A stored [K,M], B stored [K,N]
 def case_gelu(M, N, K):
     a = (torch.randn(M, K, device=dev) * 0.3).bfloat16(); b = (torch.randn(N, K, device=dev) * 0.1).bfloat16()
     bias = torch.randn(N, device=dev) * 0.1
-    out, pre = ops.gemm_bf16(a, b, bias=bias, epilogue=ops.EPI_BF16_GELU)
+    out, dact = ops.gemm_bf16(a, b, bias=bias, epilogue=ops.EPI_BF16_GELU)
     pre_ref = (a.float() @ b.float().t() + bias).bfloat16()
     act_ref = torch.nn.functional.gelu(pre_ref.float()).bfloat16()
-    return f"pre rel={rel(pre, pre_ref):.3e} act rel={rel(out, act_ref):.3e}"
+    x = pre_ref.float().requires_grad_(True)
+    torch.nn.functional.gelu(x).sum().backward()
+    return f"gelu' rel={rel(dact, x.grad):.3e} act rel={rel(out, act_ref):.3e}"
 
 def case_resid(M, N, K):
     a = torch.randn(M, K, device=dev).bfloat16(); b = torch.randn(N, K, device=dev).bfloat16()
@@ -60,7 +62,9 @@ def case_resid(M, N, K):
 def case_dgelu(M, N, K):
     a = torch.randn(M, K, device=dev).bfloat16(); b = (torch.randn(K, N, device=dev) * 0.1).bfloat16()
     pre = torch.randn(M, N, device=dev).bfloat16()
-    out = ops.gemm_bf16(a, b, b_mn_major=True, aux=pre, epilogue=ops.EPI_BF16_DGELU)
+    x = pre.float().requires_grad_(True)
+    torch.nn.functional.gelu(x).sum().backward()
+    out = ops.gemm_bf16(a, b, b_mn_major=True, aux=x.grad.bfloat16(), epilogue=ops.EPI_BF16_DGELU)
     g = (a.float() @ b.float()).bfloat16().float()
     x = pre.float().requires_grad_(True)
     torch.nn.functional.gelu(x).backward(g)
@@ -71,13 +75,19 @@ def bench(M, N, K, a_mn=False, b_mn=False, epi=ops.EPI_BF16, splits=1, iters=20)
     b = torch.randn((K, N) if b_mn else (N, K), device=dev).bfloat16()
     f32 = epi in (ops.EPI_F32, ops.EPI_F32_ATOMIC)
     out = torch.zeros(M, N, device=dev, dtype=torch.float32 if f32 else torch.bfloat16)
+    kw = {}
+    if epi == ops.EPI_BF16_DGELU:
+        kw["aux"] = torch.rand(M, N, device=dev).bfloat16()
+    if epi == ops.EPI_BF16_GELU:
+        kw["out2"] = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+        kw["bias"] = torch.randn(N, device=dev)
     for _ in range(3):
-        ops.gemm_bf16(a, b, a_mn_major=a_mn, b_mn_major=b_mn, epilogue=epi, out=out, splits=splits)
+        ops.gemm_bf16(a, b, a_mn_major=a_mn, b_mn_major=b_mn, epilogue=epi, out=out, splits=splits, **kw)
     torch.cuda.synchronize()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(iters):
-        ops.gemm_bf16(a, b, a_mn_major=a_mn, b_mn_major=b_mn, epilogue=epi, out=out, splits=splits)
+        ops.gemm_bf16(a, b, a_mn_major=a_mn, b_mn_major=b_mn, epilogue=epi, out=out, splits=splits, **kw)
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
     return f"M{M} N{N} K{K} amn{int(a_mn)} bmn{int(b_mn)} epi{epi} splits{splits}: {ms:.3f} ms {2*M*N*K/ms/1e9:.1f} TFLOP/s"
@@ -103,8 +113,15 @@ if __name__ == "__main__":
     run("bench fc2", lambda: bench(M, 1024, 4096))
     run("bench dgrad fc1", lambda: bench(M, 1024, 4096, b_mn=True))
     run("bench dgrad fc2", lambda: bench(M, 4096, 1024, b_mn=True))
-    run("bench wgrad fc1", lambda: bench(4096, 1024, M, a_mn=True, b_mn=True, epi=ops.EPI_F32_ATOMIC, splits=4))
-    run("bench wgrad o", lambda: bench(1024, 1024, M, a_mn=True, b_mn=True, epi=ops.EPI_F32_ATOMIC, splits=18))
+    run("bench dgrad fc2 dgelu", lambda: bench(M, 4096, 1024, b_mn=True, epi=ops.EPI_BF16_DGELU))
+    for sp in (4, 8, 15):
+        run("bench wgrad fc1", lambda: bench(4096, 1024, M, a_mn=True, b_mn=True, epi=ops.EPI_F32_ATOMIC, splits=sp))
+    for sp in (4, 8):
+        run("bench wgrad fc2", lambda: bench(1024, 4096, M, a_mn=True, b_mn=True, epi=ops.EPI_F32_ATOMIC, splits=sp))
+    for sp in (3, 6, 9):
+        run("bench wgrad qkv", lambda: bench(3072, 1024, M, a_mn=True, b_mn=True, epi=ops.EPI_F32_ATOMIC, splits=sp))
+    for sp in (9, 18):
+        run("bench wgrad o", lambda: bench(1024, 1024, M, a_mn=True, b_mn=True, epi=ops.EPI_F32_ATOMIC, splits=sp))
     a = torch.randn(8192, 8192, device=dev).bfloat16(); b = torch.randn(8192, 8192, device=dev).bfloat16()
     for _ in range(3): a @ b.t()
     torch.cuda.synchronize(); t0 = time.time()

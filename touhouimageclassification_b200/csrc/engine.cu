@@ -121,17 +121,19 @@ Workspace carve(const tic_vit_config* c, int B, bool training) {
   return w;
 }
 
-// Pick a split-K factor for a wgrad GEMM so that tiles * splits fills whole waves of 148 CTAs.
+// Pick a split-K factor for a wgrad GEMM so that tiles * splits fills whole waves of the 74 CTA pairs (256 x 256 output
+// tiles, one pair per tile). Fewer splits win ties: every split adds one pass of fp32 red.add traffic over the output.
 int pick_splits(int Mo, int No, int K) {
-  const int tiles = ((Mo + 127) / 128) * ((No + 255) / 256);
+  const int tiles = ((Mo + 255) / 256) * ((No + 255) / 256);
+  const int workers = 74;
   const int kblocks = (K + 63) / 64;
   int best = 1;
   double best_eff = 0.0;
-  for (int s = 1; s <= 64; ++s) {
+  for (int s = 1; s <= 32; ++s) {
     if (s > 1 && kblocks / s < 16) break;
     const long long t = static_cast<long long>(tiles) * s;
-    const double eff = static_cast<double>(t) / (static_cast<double>((t + 147) / 148) * 148.0);
-    if (eff > best_eff + 0.02) { best_eff = eff; best = s; }
+    const double eff = static_cast<double>(t) / (static_cast<double>((t + workers - 1) / workers) * workers);
+    if (eff > best_eff + 0.03) { best_eff = eff; best = s; }
   }
   return best;
 }
@@ -288,7 +290,7 @@ int vit_backward(const tic_vit_config* c, const float* P32, const void* P16v, in
 
       // fc2: x_out = xmid + act W2^T + b2        (dy = dxb, the bf16 copy of the residual-stream gradient)
       TIC_TRY(gemm_bf16(dxb, D, false, p16 + L.fc2_w, F, true, M, F, D, kEpiBf16DGelu, dact, F, nullptr, 0, nullptr, pre,
-                        F, 0, 1, st, g + L.fc1_b));  // dact <- dpre = (dy W2) * gelu'(pre); fc1 bias grad = colsum(dpre)
+                        F, 0, 1, st, g + L.fc1_b));  // dact <- dpre = (dy W2) * gelu'(pre) (saved by the forward); fc1 bias grad = colsum(dpre)
       TIC_TRY(gemm_bf16(dxb, D, true, act, F, true, D, F, M, kEpiF32Atomic, g + L.fc2_w, F, nullptr, 0, nullptr, nullptr,
                         0, 0, pick_splits(D, F, M), st));
       // fc1: pre = h2 W1^T + b1

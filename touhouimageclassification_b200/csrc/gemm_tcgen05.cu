@@ -20,6 +20,8 @@
 //   wgrad    dW = dY^T X : A = dY (MN-major)  B = X  (MN-major), split over the token dimension
 #include "tic_internal.cuh"
 
+#include <type_traits>
+
 namespace tic {
 
 namespace {
@@ -263,10 +265,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           const uint32_t taddr = tmem_base + acc_stage * BN + half * (BN / 2) + c * 32 + (static_cast<uint32_t>(quad * 32) << 16);
           tmem_ld_32x32b_x32(taddr, r);
           tmem_ld_wait();
+          const uint32_t stg_wr = smem_u32(stg) + lane * 128;
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<uint4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) =
-                make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg_wr + ((j ^ (lane & 7)) << 4)), "r"(r[4 * j]),
+                         "r"(r[4 * j + 1]), "r"(r[4 * j + 2]), "r"(r[4 * j + 3])
+                         : "memory");
         }
         __syncwarp();
         if (col < p.N) {
@@ -275,59 +279,91 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           if constexpr (EPI != kEpiF32Atomic && EPI != kEpiBf16DGelu) {
             if (p.bias != nullptr) bias = __ldg(reinterpret_cast<const float4*>(p.bias + col));
           }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int rr = 4 * i + sub_row;
-            const int row = row_base + rr;
-            if (row >= p.M) continue;
-            float4 a = *reinterpret_cast<const float4*>(stg + rr * 128 + ((ch ^ (rr & 7)) << 4));
-            a.x += bias.x; a.y += bias.y; a.z += bias.z; a.w += bias.w;
-            if constexpr (EPI == kEpiBf16) {
-              __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<long long>(row) * p.ldo + col;
-              const uint2 w = make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
-              *reinterpret_cast<uint2*>(o) = w;
-              if (p.colsum != nullptr) { csum.x += bf16_lo(w.x); csum.y += bf16_hi(w.x); csum.z += bf16_lo(w.y); csum.w += bf16_hi(w.y); }
-            } else if constexpr (EPI == kEpiBf16Gelu) {
-              // The reference evaluates GELU on the bf16-rounded fc1 output (autocast).
-              const uint32_t p0 = pack_bf16x2(a.x, a.y), p1 = pack_bf16x2(a.z, a.w);
-              if (p.out2 != nullptr)
-                *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out2) + static_cast<long long>(row) * p.ldo2 + col) =
-                    make_uint2(p0, p1);
-              *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<long long>(row) * p.ldo + col) =
-                  make_uint2(pack_bf16x2(gelu_fast(bf16_lo(p0)), gelu_fast(bf16_hi(p0))),
-                             pack_bf16x2(gelu_fast(bf16_lo(p1)), gelu_fast(bf16_hi(p1))));
-            } else if constexpr (EPI == kEpiBf16DGelu) {
-              const uint2 pre = auxh[i];
-              const float g0 = round_bf16(a.x), g1 = round_bf16(a.y), g2 = round_bf16(a.z), g3 = round_bf16(a.w);
-              const uint2 w = make_uint2(pack_bf16x2(g0 * gelu_grad_fast(bf16_lo(pre.x)), g1 * gelu_grad_fast(bf16_hi(pre.x))),
-                                         pack_bf16x2(g2 * gelu_grad_fast(bf16_lo(pre.y)), g3 * gelu_grad_fast(bf16_hi(pre.y))));
-              *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<long long>(row) * p.ldo + col) = w;
-              csum.x += bf16_lo(w.x); csum.y += bf16_hi(w.x); csum.z += bf16_lo(w.y); csum.w += bf16_hi(w.y);
-            } else if constexpr (EPI == kEpiF32Resid) {
-              // bf16 GEMM output added to the fp32 residual stream (Appendix B).
-              const float4 x = auxf[i];
-              if (!p.exact) { a.x = round_bf16(a.x); a.y = round_bf16(a.y); a.z = round_bf16(a.z); a.w = round_bf16(a.w); }
-              *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<long long>(row) * p.ldo + col) =
-                  make_float4(a.x + x.x, a.y + x.y, a.z + x.z, a.w + x.w);
-            } else if constexpr (EPI == kEpiF32Gelu) {
-              *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<long long>(row) * p.ldo + col) =
-                  make_float4(gelu_erf(a.x), gelu_erf(a.y), gelu_erf(a.z), gelu_erf(a.w));
-            } else if constexpr (EPI == kEpiF32) {
-              *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<long long>(row) * p.ldo + col) = a;
-            } else if constexpr (EPI == kEpiF32Atomic) {
-              float* o = reinterpret_cast<float*>(p.out) + static_cast<long long>(row) * p.ldo + col;
-              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w)
-                           : "memory");
-            } else if constexpr (EPI == kEpiF32PosEmbed) {
-              const int P = p.aux_int;
-              const int img = row / P, pidx = row - img * P;
-              const float4 x = auxf[i];
-              if (!p.exact) { a.x = round_bf16(a.x); a.y = round_bf16(a.y); a.z = round_bf16(a.z); a.w = round_bf16(a.w); }
-              *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) +
-                                         (static_cast<long long>(img) * (P + 1) + 1 + pidx) * p.ldo + col) =
-                  make_float4(a.x + x.x, a.y + x.y, a.z + x.z, a.w + x.w);
+          // Row pointers advance by 4 rows per step (no per-row 64-bit multiplies in the loop).
+          constexpr int kOutElem = (EPI == kEpiBf16 || EPI == kEpiBf16Gelu || EPI == kEpiBf16DGelu) ? 2 : 4;
+          const int row0 = row_base + sub_row;
+          uint8_t* po = reinterpret_cast<uint8_t*>(p.out) + (static_cast<long long>(row0) * p.ldo + col) * kOutElem;
+          const long long po_step = 4 * p.ldo * kOutElem;
+          uint8_t* po2 = nullptr;
+          long long po2_step = 0;
+          if constexpr (EPI == kEpiBf16Gelu) {
+            if (p.out2 != nullptr) {
+              po2 = reinterpret_cast<uint8_t*>(p.out2) + (static_cast<long long>(row0) * p.ldo2 + col) * 2;
+              po2_step = 8 * p.ldo2;
             }
           }
+          const uint32_t stg_rd = smem_u32(stg) + sub_row * 128;
+          // Branch-free over the 8 rows (only the stores are predicated) so that their dependency chains interleave:
+          // a per-row `continue` serialised the rows and left the epilogue latency-bound.
+          auto rows = [&](auto save_grad_tag) {
+            constexpr bool kSaveGrad = decltype(save_grad_tag)::value;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int rr = 4 * i + sub_row;
+              const int row = row0 + 4 * i;
+              const bool ok = row < p.M;
+              uint8_t* o = po + i * po_step;
+              float4 a;
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                           : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w)
+                           : "r"(stg_rd + i * 512 + ((ch ^ (rr & 7)) << 4)));
+              a.x += bias.x; a.y += bias.y; a.z += bias.z; a.w += bias.w;
+              if constexpr (EPI == kEpiBf16) {
+                const uint2 w = make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
+                if (ok) *reinterpret_cast<uint2*>(o) = w;
+                if (p.colsum != nullptr && ok) {
+                  csum.x += bf16_lo(w.x); csum.y += bf16_hi(w.x); csum.z += bf16_lo(w.y); csum.w += bf16_hi(w.y);
+                }
+              } else if constexpr (EPI == kEpiBf16Gelu) {
+                // The reference evaluates GELU on the bf16-rounded fc1 output (autocast). What the
+                // backward needs from this layer is only GELU'(pre), so that is what out2 keeps (bf16), not pre itself.
+                const uint32_t p0 = pack_bf16x2(a.x, a.y), p1 = pack_bf16x2(a.z, a.w);
+                float y0, y1, y2, y3;
+                if constexpr (kSaveGrad) {
+                  float g0, g1, g2, g3;
+                  gelu_and_grad_fast(bf16_lo(p0), y0, g0); gelu_and_grad_fast(bf16_hi(p0), y1, g1);
+                  gelu_and_grad_fast(bf16_lo(p1), y2, g2); gelu_and_grad_fast(bf16_hi(p1), y3, g3);
+                  if (ok) *reinterpret_cast<uint2*>(po2 + i * po2_step) = make_uint2(pack_bf16x2(g0, g1), pack_bf16x2(g2, g3));
+                } else {
+                  y0 = gelu_fast(bf16_lo(p0)); y1 = gelu_fast(bf16_hi(p0)); y2 = gelu_fast(bf16_lo(p1)); y3 = gelu_fast(bf16_hi(p1));
+                }
+                if (ok) *reinterpret_cast<uint2*>(o) = make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
+              } else if constexpr (EPI == kEpiBf16DGelu) {
+                // aux = GELU'(pre) saved by the forward epilogue; autograd's product is rounded to bf16 once more.
+                const uint2 gp = ok ? auxh[i] : make_uint2(0u, 0u);
+                const uint32_t d0 = pack_bf16x2(a.x, a.y), d1 = pack_bf16x2(a.z, a.w);
+                const uint2 w = make_uint2(pack_bf16x2(bf16_lo(d0) * bf16_lo(gp.x), bf16_hi(d0) * bf16_hi(gp.x)),
+                                           pack_bf16x2(bf16_lo(d1) * bf16_lo(gp.y), bf16_hi(d1) * bf16_hi(gp.y)));
+                if (ok) *reinterpret_cast<uint2*>(o) = w;
+                csum.x += bf16_lo(w.x); csum.y += bf16_hi(w.x); csum.z += bf16_lo(w.y); csum.w += bf16_hi(w.y);
+              } else if constexpr (EPI == kEpiF32Resid) {
+                // bf16 GEMM output added to the fp32 residual stream (Appendix B).
+                const float4 x = auxf[i];
+                if (!p.exact) { a.x = round_bf16(a.x); a.y = round_bf16(a.y); a.z = round_bf16(a.z); a.w = round_bf16(a.w); }
+                if (ok) *reinterpret_cast<float4*>(o) = make_float4(a.x + x.x, a.y + x.y, a.z + x.z, a.w + x.w);
+              } else if constexpr (EPI == kEpiF32Gelu) {
+                if (ok) *reinterpret_cast<float4*>(o) = make_float4(gelu_erf(a.x), gelu_erf(a.y), gelu_erf(a.z), gelu_erf(a.w));
+              } else if constexpr (EPI == kEpiF32) {
+                if (ok) *reinterpret_cast<float4*>(o) = a;
+              } else if constexpr (EPI == kEpiF32Atomic) {
+                if (ok)
+                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w)
+                               : "memory");
+              } else if constexpr (EPI == kEpiF32PosEmbed) {
+                if (ok) {
+                  const int P = p.aux_int;
+                  const int img = row / P, pidx = row - img * P;
+                  const float4 x = auxf[i];
+                  if (!p.exact) { a.x = round_bf16(a.x); a.y = round_bf16(a.y); a.z = round_bf16(a.z); a.w = round_bf16(a.w); }
+                  *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) +
+                                             (static_cast<long long>(img) * (P + 1) + 1 + pidx) * p.ldo + col) =
+                      make_float4(a.x + x.x, a.y + x.y, a.z + x.z, a.w + x.w);
+                }
+              }
+            }
+          };
+          if (po2 != nullptr) rows(std::true_type{});
+          else rows(std::false_type{});
           if constexpr (EPI == kEpiBf16DGelu || EPI == kEpiBf16) {
             if (p.colsum != nullptr) {  // lanes with the same 4-column group (lane & 7) hold partial sums over 8 rows each
 #pragma unroll

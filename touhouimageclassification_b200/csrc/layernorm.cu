@@ -67,7 +67,7 @@ ln_fwd_kernel(const float* __restrict__ x, long long ldx, const float* __restric
 // shared memory (keeps the register count low enough for 3 CTAs / SM), reduced across the CTA's warps at
 // the end, then one atomicAdd per column per CTA.
 template <int VEC>
-__global__ void __launch_bounds__(LN_WARPS * 32)
+__global__ void __launch_bounds__(LN_WARPS * 32, 2)
 ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long lddy, const float* __restrict__ x, long long ldx,
               const float* __restrict__ mean_in, const float* __restrict__ rstd_in, const float* __restrict__ gamma,
               const float* dres, long long lddres, int rows, float* dx, long long lddx,
@@ -93,21 +93,36 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long lddy, const float*
     const float mean = mean_in[row], rstd = rstd_in[row];
     const float4* xr = reinterpret_cast<const float4*>(x + static_cast<long long>(row) * ldx);
     const uint2* dyr = reinterpret_cast<const uint2*>(dy + static_cast<long long>(row) * lddy);
-    float4 xh[VEC], gg[VEC];
+    const float4* rr = dres ? reinterpret_cast<const float4*>(dres + static_cast<long long>(row) * lddres) : nullptr;
+    // All of the row's HBM reads (x, dy and the residual gradient) are issued up front: 10 KB in flight per warp
+    // instead of two dependent round trips. xhat and dy * gamma are recomputed in the second pass rather than kept,
+    // which holds the kernel at 2 CTAs / SM.
+    float4 xv[VEC], rv[VEC];
+    uint2 dv[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      xv[i] = xr[lane + 32 * i];
+      dv[i] = dyr[lane + 32 * i];
+    }
+    if (rr != nullptr) {
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) rv[i] = rr[lane + 32 * i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
-      const float4 xv = xr[lane + 32 * i];
-      const uint2 dv = dyr[lane + 32 * i];
       const float4 gm = __ldg(g4 + lane + 32 * i);
-      const float d0 = bf16_lo(dv.x), d1 = bf16_hi(dv.x), d2 = bf16_lo(dv.y), d3 = bf16_hi(dv.y);
-      xh[i].x = (xv.x - mean) * rstd; xh[i].y = (xv.y - mean) * rstd;
-      xh[i].z = (xv.z - mean) * rstd; xh[i].w = (xv.w - mean) * rstd;
-      gg[i].x = d0 * gm.x; gg[i].y = d1 * gm.y; gg[i].z = d2 * gm.z; gg[i].w = d3 * gm.w;
-      s1 += (gg[i].x + gg[i].y) + (gg[i].z + gg[i].w);
-      s2 += (gg[i].x * xh[i].x + gg[i].y * xh[i].y) + (gg[i].z * xh[i].z + gg[i].w * xh[i].w);
+      const float d0 = bf16_lo(dv[i].x), d1 = bf16_hi(dv[i].x), d2 = bf16_lo(dv[i].y), d3 = bf16_hi(dv[i].y);
+      const float h0 = (xv[i].x - mean) * rstd, h1 = (xv[i].y - mean) * rstd;
+      const float h2 = (xv[i].z - mean) * rstd, h3 = (xv[i].w - mean) * rstd;
+      const float g0 = d0 * gm.x, g1 = d1 * gm.y, g2 = d2 * gm.z, g3 = d3 * gm.w;
+      s1 += (g0 + g1) + (g2 + g3);
+      s2 += (g0 * h0 + g1 * h1) + (g2 * h2 + g3 * h3);
       float4 ag = my_g[lane + 32 * i], ab = my_b[lane + 32 * i];
-      ag.x += d0 * xh[i].x; ag.y += d1 * xh[i].y; ag.z += d2 * xh[i].z; ag.w += d3 * xh[i].w;
+      ag.x += d0 * h0; ag.y += d1 * h1; ag.z += d2 * h2; ag.w += d3 * h3;
       ab.x += d0; ab.y += d1; ab.z += d2; ab.w += d3;
       my_g[lane + 32 * i] = ag;
       my_b[lane + 32 * i] = ab;
@@ -115,15 +130,15 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long lddy, const float*
     const float c1 = warp_sum(s1) * (1.0f / D), c2 = warp_sum(s2) * (1.0f / D);
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
+      const float4 gm = __ldg(g4 + lane + 32 * i);
+      const float d0 = bf16_lo(dv[i].x), d1 = bf16_hi(dv[i].x), d2 = bf16_lo(dv[i].y), d3 = bf16_hi(dv[i].y);
+      const float h0 = (xv[i].x - mean) * rstd, h1 = (xv[i].y - mean) * rstd;
+      const float h2 = (xv[i].z - mean) * rstd, h3 = (xv[i].w - mean) * rstd;
       float4 o;
-      o.x = rstd * (gg[i].x - c1 - xh[i].x * c2);
-      o.y = rstd * (gg[i].y - c1 - xh[i].y * c2);
-      o.z = rstd * (gg[i].z - c1 - xh[i].z * c2);
-      o.w = rstd * (gg[i].w - c1 - xh[i].w * c2);
-      if (dres) {
-        const float4 r = reinterpret_cast<const float4*>(dres + static_cast<long long>(row) * lddres)[lane + 32 * i];
-        o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
-      }
+      o.x = rstd * (d0 * gm.x - c1 - h0 * c2) + rv[i].x;
+      o.y = rstd * (d1 * gm.y - c1 - h1 * c2) + rv[i].y;
+      o.z = rstd * (d2 * gm.z - c1 - h2 * c2) + rv[i].z;
+      o.w = rstd * (d3 * gm.w - c1 - h3 * c2) + rv[i].w;
       reinterpret_cast<float4*>(dx + static_cast<long long>(row) * lddx)[lane + 32 * i] = o;
       if (dx_bf16) {
         uint2 w;

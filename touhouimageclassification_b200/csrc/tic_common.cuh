@@ -43,38 +43,44 @@ TIC_DEVINL float gelu_erf_grad(float x) {
   const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
   return cdf + x * pdf;
 }
-// Same functions for the GEMM epilogues, whose results are rounded to bf16: erfc via Abramowitz-Stegun 7.1.26
-// (|error| < 1.5e-7, far below bf16 resolution) with one MUFU.RCP + one MUFU.EX2 shared by cdf and pdf.
-//   half_erfc = 0.5 * erfc(|x| / sqrt(2)) = 0.5 * t * (a1 + t (a2 + t (a3 + t (a4 + t a5)))) * exp(-x^2 / 2)
-TIC_DEVINL void gelu_parts(float x, float& cdf, float& e) {
-  const float u = fabsf(x) * 0.70710678118654752440f;
-  float t;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, u, 1.0f)));
-  e = exp2f(x * x * -0.72134752044448170368f);  // exp(-x^2 / 2)
-  float poly = fmaf(t, 1.061405429f, -1.453152027f);
-  poly = fmaf(t, poly, 1.421413741f);
-  poly = fmaf(t, poly, -0.284496736f);
-  poly = fmaf(t, poly, 0.254829592f);
-  const float half_erfc = 0.5f * t * poly * e;
-  cdf = x >= 0.f ? 1.0f - half_erfc : half_erfc;
-}
-TIC_DEVINL float gelu_fast(float x) {
-  float cdf, e;
-  gelu_parts(x, cdf, e);
-  return x * cdf;
-}
-TIC_DEVINL float gelu_grad_fast(float x) {
-  float cdf, e;
-  gelu_parts(x, cdf, e);
-  return fmaf(x * 0.39894228040143267794f, e, cdf);
-}
-
-// 2^x on the SFU (MUFU.EX2), flush-to-zero, no range fix-ups: inputs here are <= 0 (softmax exponents).
+// 2^x on the SFU (MUFU.EX2), flush-to-zero, no range fix-ups: inputs here are <= 0 (softmax / Gaussian exponents).
 TIC_DEVINL float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+
+// GELU(x) = x Phi(x) and its derivative Phi(x) + x phi(x) for the GEMM epilogues, whose results are rounded to bf16
+// (resolution 2^-9): erfc via Abramowitz-Stegun 7.1.25 (|error| <= 2.5e-5 on erf, i.e. 1.3e-5 on Phi) with one MUFU.RCP
+// and one MUFU.EX2 shared by cdf and pdf, constants folded so that the value costs 11 and value + derivative 15 FP32
+// instructions (the epilogue of the fc1 GEMM is bound by instruction issue, not by the tensor pipe):
+//   h = 0.5 erfc(|x| / sqrt 2) = t (a1' + t (a2' + t a3')) exp(-x^2 / 2),   t = 1 / (1 + p |x| / sqrt 2)
+//   gelu(x) = max(x, 0) - |x| h,      gelu'(x) = (x >= 0 ? 1 - h : h) + x exp(-x^2 / 2) / sqrt(2 pi)
+TIC_DEVINL void gelu_core(float x, float& h, float& e) {
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(fabsf(x), 0.47047f * 0.70710678118654752440f, 1.0f)));
+  e = ex2_approx(x * (x * -0.72134752044448170368f));  // exp(-x^2 / 2)
+  float q = fmaf(t, 0.5f * 0.7478556f, 0.5f * -0.0958798f);
+  q = fmaf(t, q, 0.5f * 0.3480242f);
+  h = (q * t) * e;
+}
+TIC_DEVINL float gelu_fast(float x) {
+  float h, e;
+  gelu_core(x, h, e);
+  return fmaf(-fabsf(x), h, fmaxf(x, 0.f));
+}
+TIC_DEVINL float gelu_grad_fast(float x) {
+  float h, e;
+  gelu_core(x, h, e);
+  return fmaf(x * 0.39894228040143267794f, e, x >= 0.f ? 1.0f - h : h);
+}
+TIC_DEVINL void gelu_and_grad_fast(float x, float& y, float& g) {
+  float h, e;
+  gelu_core(x, h, e);
+  y = fmaf(-fabsf(x), h, fmaxf(x, 0.f));
+  g = fmaf(x * 0.39894228040143267794f, e, x >= 0.f ? 1.0f - h : h);
+}
+
 
 TIC_DEVINL float warp_sum(float v) {
 #pragma unroll

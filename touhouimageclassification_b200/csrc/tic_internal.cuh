@@ -21,9 +21,9 @@ struct ProfScope {
 // GEMM epilogues (values are part of the C-ABI: TIC_EPI_* in include/tic_b200.h)
 enum Epilogue : int {
   kEpiBf16 = 0,         // out bf16 = acc (+bias)
-  kEpiBf16Gelu = 1,     // out2 bf16 = pre = bf16(acc + bias); out bf16 = gelu(pre)
+  kEpiBf16Gelu = 1,     // pre = bf16(acc + bias); out bf16 = gelu(pre); out2 bf16 (optional) = gelu'(pre), kept for backward
   kEpiF32Resid = 2,     // out f32 = bf16(acc + bias) + aux_f32[m,n]
-  kEpiBf16DGelu = 3,    // out bf16 = bf16(acc) * gelu'(aux_bf16[m,n])
+  kEpiBf16DGelu = 3,    // out bf16 = bf16(acc) * aux_bf16[m,n], aux = gelu'(pre) saved by kEpiBf16Gelu
   kEpiF32 = 4,          // out f32 = acc (+bias)
   kEpiF32Atomic = 5,    // out f32 += acc (split-K partial, red.global.add)
   kEpiF32PosEmbed = 6,  // patch embedding rows: see tic_b200.h
