@@ -302,10 +302,48 @@ def run_ours(args):
                h2d_bytes_per_step=(x_host.numel() * 4 + y_host.numel() * 8) * world, d2h_bytes_per_step=4 * world,
                api="touhouimageclassification_b200.finetune.train_step(model, (x_host, y_host), FusedAdamW, CrossEntropyLoss)")
 
+    # ---- batched inference (BASELINE config 4: utils/filter + web serve path), per-GPU replica, device-resident inputs
+    inference = None
+    if not args.no_inference:
+        del trainer
+        model._workspaces.clear()            # drop the 46 GB training workspace before the batch-1024 forwards
+        torch.cuda.empty_cache()
+        model.eval()
+        fwd_flops = flops_per_image_forward(WORKLOAD)
+        inference = dict(unit="img/s", dtype="bf16", note="ViT-L/16 224x224 forward (engine_forward), inputs resident in HBM, "
+                         "CUDA events, per GPU replica", batches={})
+
+        def time_forward(fn, iters):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            a, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(iters):
+                fn()
+            b2.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b2) / iters
+
+        with torch.no_grad():
+            for bs in (1, 8, 64, 256, 1024):
+                xb = torch.randn(bs, 3, S, S, device=dev, generator=g)
+                ms = time_forward(lambda: model.engine_forward(xb, training=False), 20 if bs <= 64 else 5)
+                ips = bs / (ms / 1e3)
+                inference["batches"][str(bs)] = dict(ms=round(ms, 4), img_per_s=round(ips, 1),
+                                                     frac_of_burst_peak=round(ips * fwd_flops / 1e12 / peaks["bf16_tflops"], 4))
+            model.set_precision("fp32")        # the reference's no-autocast serving arithmetic (serve.py:99-101)
+            xb = torch.randn(64, 3, S, S, device=dev, generator=g)
+            ms = time_forward(lambda: model.engine_forward_f32(xb), 3)
+            inference["fp32_mode_batch64"] = dict(ms=round(ms, 3), img_per_s=round(64 / (ms / 1e3), 1))
+            model.set_precision("bf16")
+
     if rank == 0:
         line = base_line(args, n_gpus=world)
         line.update(value=value, ms_per_step=ms_step, e2e=e2e, roofline=roofline, gpu_launches=int(launches),
                     clocks=clocks.summary(), loss=loss_val)
+        if inference is not None:
+            line["inference"] = inference
         if world == 1 and not args.no_cpu_baseline:
             v, ms, kind, cores, sample = cpu_train_steps(steps=2, warmup=1, time_budget_s=60.0)
             line["cpu_baseline"] = dict(value=v, unit="img/s", cores=cores, kind=kind, sample=sample)
@@ -340,6 +378,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-inference", action="store_true", help="skip the batched-inference sweep after the training bench")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -136,6 +136,17 @@ TIC_API int tic_adamw_step(float* p, const float* g, float* m, float* v, void* s
 /* ---- elementwise glue ---------------------------------------------------------------------------- */
 /* fp32 NCHW [B,3,S,S] -> bf16 patch rows [B*(S/16)^2, 768], K ordered (c, py, px) (modeling_vit.py:151,166 [a2]) */
 TIC_API int tic_patchify_f32(const float* pixels, void* patches_bf16, int B, int S, void* stream);
+/* CutMix / MixUp of a device batch (torchvision v2 RandomChoice([CutMix, MixUp]), ntrain.py:30-33,45-46 [a19]) fused
+ * with the patchify: sample b is paired with sample b-1 (roll(1,0)). mode 0 = none, 1 = MixUp with weight lam,
+ * 2 = CutMix pasting the box [y1,y2) x [x1,x2) from the rolled batch. mixed_out (fp32 [B,3,S,S], optional, must not
+ * alias pixels) and patches_bf16 ([B*(S/16)^2, 768], optional) receive the result; the fp32 arithmetic is bit-exact
+ * with the three torch ops of the reference. tic_mix_targets writes the soft labels
+ * onehot(y[b-1]) * one_minus_lam + onehot(y[b]) * lam (lam = the box-adjusted lambda for CutMix). lam and
+ * one_minus_lam are passed separately so the host can round each from its own double, as torch does. */
+TIC_API int tic_mix_patchify_f32(const float* pixels, float* mixed_out, void* patches_bf16, int B, int S, int mode,
+                                 float lam, float one_minus_lam, int x1, int y1, int x2, int y2, void* stream);
+TIC_API int tic_mix_targets(const int64_t* labels, int B, int C, float lam, float one_minus_lam, float* soft_out,
+                            void* stream);
 TIC_API int tic_cast_f32_to_bf16(const float* src, void* dst_bf16, int64_t n, void* stream);
 TIC_API int tic_cast_bf16_to_f32(const void* src_bf16, float* dst, int64_t n, void* stream);
 /* out[n] += sum_m dy[m, n] (bias gradients) */

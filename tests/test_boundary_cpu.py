@@ -84,6 +84,7 @@ def test_requires_grad_false_on_backbone_like_ntrain():
 
 def test_lmodule_surface():
     from touhouimageclassification_b200.ntrain import ViTLModule, cutmix_or_mixup
+    from oracle import vit_oracle as O
     lm = ViTLModule(120, False, "google/vit-base-patch16-224", lr=1e-5, weight_decay=0.01, full_finetune=False)
     keys = list(lm.state_dict().keys())
     assert keys[0] == "vit.vit.embeddings.cls_token" and keys[-1] == "vit.classifier.bias"  # Lightning ckpt prefix
@@ -92,21 +93,33 @@ def test_lmodule_surface():
     torch.manual_seed(0)
     x = torch.randn(4, 3, 8, 8)
     y = torch.tensor([0, 1, 2, 3])
-    x2, y2 = cutmix_or_mixup(x, y, 5)
+    x2, y2 = O.cutmix_or_mixup(x, y, 5)
     assert x2.shape == x.shape and y2.shape == (4, 5)
     torch.testing.assert_close(y2.sum(1), torch.ones(4))
+    with pytest.raises(RuntimeError):   # the product path is CUDA only
+        cutmix_or_mixup(x, y, 5)
 
 
 def test_mixup_cutmix_match_torchvision():
     v2 = pytest.importorskip("torchvision.transforms.v2")
-    from touhouimageclassification_b200.ntrain import cutmix_or_mixup
+    from touhouimageclassification_b200.ntrain import draw_mix
+    from oracle import vit_oracle as O
     x = torch.randn(6, 3, 16, 16)
     y = torch.tensor([0, 1, 2, 3, 4, 0])
     ref = v2.RandomChoice([v2.CutMix(num_classes=5), v2.MixUp(num_classes=5)])
-    for seed in range(6):
+    for seed in range(8):
         torch.manual_seed(seed)
         xr, yr = ref(x, y)
         torch.manual_seed(seed)
-        xo, yo = cutmix_or_mixup(x, y, 5)
-        torch.testing.assert_close(xo, xr)
-        torch.testing.assert_close(yo, yr)
+        xo, yo = O.cutmix_or_mixup(x, y, 5)          # the oracle's restatement is torchvision's, bit for bit
+        assert torch.equal(xo, xr) and torch.equal(yo, yr)
+        # the product's host-side sampler draws the same numbers in the same order and derives the same box
+        torch.manual_seed(seed)
+        kind, lam, r_x, r_y = O.draw_mix(16, 16)
+        torch.manual_seed(seed)
+        mode, lam2, box, lam_label = draw_mix(16, 16)
+        assert lam2 == lam and mode == (2 if kind == "cutmix" else 1)
+        if kind == "cutmix":
+            assert (*box, lam_label) == O.cutmix_box(16, 16, lam, r_x, r_y)
+        else:
+            assert lam_label == lam

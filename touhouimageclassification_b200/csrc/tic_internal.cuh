@@ -46,6 +46,9 @@ int layernorm_bwd(const void* dy_bf16, long long lddy, const float* x, long long
 
 // elementwise.cu
 int patchify_f32(const float* x, void* out_bf16, int B, int S, cudaStream_t stream);
+int mix_patchify_f32(const float* x, float* mixed, void* out_bf16, int B, int S, int mode, float lam, float one_minus_lam,
+                     int x1, int y1, int x2, int y2, cudaStream_t stream);
+int mix_targets(const long long* y, int B, int C, float lam, float one_minus_lam, float* soft, cudaStream_t stream);
 int cls_rows(const float* cls, const float* pos, float* x, int B, int N, int D, cudaStream_t stream);
 int embed_bwd(const float* dx, int B, int N, int D, float* dpos, float* dcls, void* dpatch_bf16, cudaStream_t stream);
 int cast_f32_to_bf16(const float* src, void* dst, long long n, cudaStream_t stream);

@@ -12,6 +12,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import ops
 from .finetune import fused_train_step
 from .model import ViT
 from .optim import FusedAdamW
@@ -23,36 +24,34 @@ except Exception:  # ImportError or a broken install
     _Base = nn.Module
 
 
-def mixup(x, y, num_classes, lam):
-    """torchvision v2 MixUp (``_augment.py:214-219,249-267``): pair sample i with i-1, blend images and one-hot labels."""
-    yo = F.one_hot(y, num_classes).to(x.dtype) if y.dim() == 1 else y
-    return x.roll(1, 0).mul(1.0 - lam).add_(x.mul(lam)), yo.roll(1, 0).mul(1.0 - lam).add_(yo.mul(lam))
-
-
-def cutmix(x, y, num_classes, lam, r_x, r_y):
-    """torchvision v2 CutMix (``_augment.py:298-337``): paste a box from the rolled batch, labels by box area."""
-    H, W = x.shape[-2:]
-    r = 0.5 * (1.0 - lam) ** 0.5
-    r_w_half, r_h_half = int(r * W), int(r * H)
-    x1, y1 = max(r_x - r_w_half, 0), max(r_y - r_h_half, 0)
-    x2, y2 = min(r_x + r_w_half, W), min(r_y + r_h_half, H)
-    lam_adj = float(1.0 - (x2 - x1) * (y2 - y1) / (W * H))
-    out = x.clone()
-    out[..., y1:y2, x1:x2] = x.roll(1, 0)[..., y1:y2, x1:x2]
-    yo = F.one_hot(y, num_classes).to(x.dtype) if y.dim() == 1 else y
-    return out, yo.roll(1, 0).mul(1.0 - lam_adj).add_(yo.mul(lam_adj))
-
-
-def cutmix_or_mixup(x, y, num_classes):
-    """``v2.RandomChoice([CutMix, MixUp])`` (ntrain.py:30-33): same RNG draws, in the same order, as torchvision."""
-    idx = int(torch.multinomial(torch.tensor([0.5, 0.5]), 1))          # _container.py:152
+def draw_mix(H: int, W: int):
+    """RNG draws of ``v2.RandomChoice([CutMix, MixUp])`` (ntrain.py:30-33), same generator, same order as torchvision
+    (``_container.py:152``; Beta(1,1) then the box centre, ``_augment.py:249-267,298-337``). Returns the kernel
+    arguments: (mode, lam_image, box, lam_label) with mode 1 = MixUp, 2 = CutMix."""
+    idx = int(torch.multinomial(torch.tensor([0.5, 0.5]), 1))
     lam = float(torch.distributions.Beta(torch.tensor([1.0]), torch.tensor([1.0])).sample(()))
     if idx == 0:
-        H, W = x.shape[-2:]
         r_x = int(torch.randint(W, size=(1,)))
         r_y = int(torch.randint(H, size=(1,)))
-        return cutmix(x, y, num_classes, lam, r_x, r_y)
-    return mixup(x, y, num_classes, lam)
+        r = 0.5 * (1.0 - lam) ** 0.5
+        r_w_half, r_h_half = int(r * W), int(r * H)
+        x1, y1 = max(r_x - r_w_half, 0), max(r_y - r_h_half, 0)
+        x2, y2 = min(r_x + r_w_half, W), min(r_y + r_h_half, H)
+        lam_adj = float(1.0 - (x2 - x1) * (y2 - y1) / (W * H))
+        return 2, lam, (x1, y1, x2, y2), lam_adj
+    return 1, lam, (0, 0, 0, 0), lam
+
+
+def cutmix_or_mixup(x, y, num_classes, want_pixels=True, want_patches=False):
+    """``self.cutmix_or_mixup(x, y)`` of the reference's ``training_step`` (ntrain.py:45-46) on the device: ONE kernel
+    blends / pastes the rolled batch (bit-exact with torchvision's fp32 ops) and can emit the bf16 patch rows the engine
+    consumes, a second tiny kernel writes the soft labels. Returns (pixels | None, soft_labels, patches | None)."""
+    if not x.is_cuda:
+        raise RuntimeError("cutmix_or_mixup runs on CUDA tensors only (there is no CPU fallback)")
+    if y.dim() != 1:
+        raise ValueError("labels must be a 1-D tensor of class indices (torchvision v2 CutMix / MixUp contract)")
+    mode, lam, box, lam_label = draw_mix(*x.shape[-2:])
+    return ops.mix_batch(x, y, num_classes, mode, lam, box, lam_label, want_pixels=want_pixels, want_patches=want_patches)
 
 
 class ViTLModule(_Base):
@@ -82,7 +81,7 @@ class ViTLModule(_Base):
     def training_step(self, batch, batch_idx):
         x, y = batch
         if self.enable_mixup:
-            x, y = cutmix_or_mixup(x, y, self.num_classes)
+            x, y, _ = cutmix_or_mixup(x, y, self.num_classes)
         logits = self.vit(x).logits
         loss = F.cross_entropy(logits.float(), y)
         self.log('train_loss', loss, prog_bar=True)
@@ -91,9 +90,11 @@ class ViTLModule(_Base):
     def fused_training_step(self, batch, optimizer: FusedAdamW, grad_sync=None, world_size: int = 1):
         """training_step + backward + optimizer step in one engine pass (manual-optimization fast path)."""
         x, y = batch
-        if self.enable_mixup:
-            x, y = cutmix_or_mixup(x, y, self.num_classes)
-        loss = fused_train_step(self.vit, optimizer, x, y, grad_sync=grad_sync, world_size=world_size)
+        patches = None
+        if self.enable_mixup:  # the mixed image is never materialised: the kernel writes the bf16 patch rows directly
+            _, y, patches = cutmix_or_mixup(x, y, self.num_classes, want_pixels=False, want_patches=True)
+            x = None
+        loss = fused_train_step(self.vit, optimizer, x, y, patches=patches, grad_sync=grad_sync, world_size=world_size)
         self.log('train_loss', loss, prog_bar=True)
         return loss
 

@@ -156,6 +156,27 @@ def patchify_f32(x):
     return out
 
 
+def mix_batch(x, y, num_classes, mode, lam, box, lam_label, want_pixels=True, want_patches=False):
+    """CutMix (mode 2) / MixUp (mode 1) of a device batch against its roll(1, 0), fused with the patchify.
+    Returns (mixed fp32 pixels | None, soft labels fp32 [B, C], bf16 patch rows | None)."""
+    _require_cuda(x, y)
+    B, _, S, _ = x.shape
+    xs = x.detach()
+    if xs.dtype != torch.float32 or not xs.is_contiguous():
+        xs = xs.float().contiguous()
+    mixed = torch.empty_like(xs) if want_pixels else None
+    patches = torch.empty((B * (S // 16) ** 2, 768), device=x.device, dtype=torch.bfloat16) if want_patches else None
+    x1, y1, x2, y2 = box
+    lib = _lib.load()
+    _lib.check(lib.tic_mix_patchify_f32(_p(xs), _p(mixed), _p(patches), c_int(B), c_int(S), c_int(mode), c_float(lam),
+                                        c_float(1.0 - lam), c_int(x1), c_int(y1), c_int(x2), c_int(y2), _s()))
+    soft = torch.empty((B, num_classes), device=x.device, dtype=torch.float32)
+    yl = y.long().contiguous()
+    _lib.check(lib.tic_mix_targets(_p(yl), c_int(B), c_int(num_classes), c_float(lam_label), c_float(1.0 - lam_label),
+                                   _p(soft), _s()))
+    return mixed, soft, patches
+
+
 def colsum_bf16(dy):
     _require_cuda(dy)
     rows, cols = dy.shape
