@@ -1,6 +1,7 @@
 """Dev tool: per-phase clock stamps of the fused attention backward (TIC_FB_TRACE=1)."""
 import os, sys
 os.environ["TIC_FB_TRACE"] = "1"
+os.environ["TIC_FF_TRACE"] = "1"
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from touhouimageclassification_b200 import ops

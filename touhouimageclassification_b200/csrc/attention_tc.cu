@@ -481,7 +481,11 @@ int attention_fwd_tc(const void* q, const void* k, const void* v, long long ld, 
       (reinterpret_cast<uintptr_t>(v) & 15))
     return set_error(kErrInvalidArg, "attention: q/k/v must be 16-byte aligned with a pitch that is a multiple of 8");
   ProfScope prof("attention_fwd", 4.0 * B * H * static_cast<double>(N) * N * AT_HD, 8.0 * B * H * static_cast<double>(N) * AT_HD, stream);
-  if (N <= 224) return launch_fwd<224>(q, k, v, ld, o, ldo, lse, B, N, H, scale, stream);
+  if (N <= 224) {
+    if ((ldo % 8) || (reinterpret_cast<uintptr_t>(o) & 15))
+      return set_error(kErrInvalidArg, "attention: o must be 16-byte aligned with a pitch that is a multiple of 8");
+    return attention_fwd_fused(q, k, v, ld, o, ldo, lse, B, N, H, scale, stream);  // persistent, one key block
+  }
   return launch_fwd<128>(q, k, v, ld, o, ldo, lse, B, N, H, scale, stream);
 }
 

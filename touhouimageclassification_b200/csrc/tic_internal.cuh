@@ -92,6 +92,9 @@ int attention_bwd_tc(const void* q, const void* k, const void* v, long long ld, 
                      const void* dout, long long lddo, const float* lse, float* delta, void* dq, void* dk, void* dv,
                      long long lddqkv, int B, int N, int H, int head_dim, float scale, cudaStream_t stream,
                      float* bias_grad = nullptr, int bias_mask = 7);
+// attention_fwd_fused.cu (N <= 224: persistent kernel, both query tiles of a head per CTA, operands prefetched)
+int attention_fwd_fused(const void* q, const void* k, const void* v, long long ld, void* o, long long ldo, float* lse, int B,
+                        int N, int H, float scale, cudaStream_t stream);
 // attention_bwd_fused.cu
 int attention_bwd_fused(const void* q, const void* k, const void* v, long long ld, const void* o, long long ldo,
                         const void* dout, long long lddo, const float* lse, void* dq, void* dk, void* dv, long long ldg,
