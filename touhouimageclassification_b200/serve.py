@@ -6,8 +6,10 @@ bf16 tensor-core engine and ``predict_batch`` does one device->host copy per bat
 """
 from __future__ import annotations
 
+import os
+import queue
 import threading
-from typing import Sequence
+from typing import Callable, List, Sequence
 
 import torch
 
@@ -118,3 +120,219 @@ def predict_batch(model: ViTForImageClassification, image_batch: torch.Tensor, i
                 k = int(k)
                 results.append((idx_to_class[k] if idx_to_class is not None else k, c))
     return results
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Batched full_judge / filter pipeline (TIC/utils/serve.py:158-230, TIC/utils/filter.py:17-27) [section 8f rank 2]
+# ----------------------------------------------------------------------------------------------------------------------
+IMAGE_EXTENSIONS = ('.jpg', '.jpeg', '.png', '.bmp', '.gif')
+
+
+def full_judge(model, transforms, class_to_idx, args=None, image=None, device=None, output=None, batch_size: int = 1024,
+               mean=None, std=None):
+    """``serve.full_judge``: walk ``image`` (a file or a class-per-directory tree), predict every picture, write the
+    reference's CSV (``filename,predicted_class,confidence,actual_class,correct,path``) and return the accuracy.
+
+    The reference forwards one image at a time with a host sync per image; here pictures are decoded on the host,
+    stacked into batches of up to ``batch_size`` and forwarded together (one device->host copy per batch). With
+    ``transforms=None`` and ``mean`` / ``std`` given, same-sized pictures skip the CPU transform entirely: their uint8
+    pixels go to the GPU and ``preprocess_u8`` resizes, normalises and patchifies them in one kernel."""
+    from PIL import Image
+    if args:
+        image, device, output = args.image, args.device, args.output
+    device = device or 'cuda'
+    idx_to_class = {v: k for k, v in class_to_idx.items()}
+    if os.path.isfile(image):
+        tensor = transforms(Image.open(image).convert('RGB')).unsqueeze(0)
+        predicted_class, confidence = serve(model, tensor, class_to_idx, device)
+        if not output:
+            print(f"Prediction: {predicted_class} (Confidence: {confidence:.4f})")
+        return None
+    files = []
+    for root, _dirs, names in os.walk(image):
+        for name in names:
+            if os.path.splitext(name)[1].lower() in IMAGE_EXTENSIONS:
+                files.append((name, os.path.basename(root), os.path.join(root, name)))
+    print(f"Total images to process: {len(files)}")
+    out = open(output, 'w') if output else None
+    if out:
+        print("filename,predicted_class,confidence,actual_class,correct,path", file=out)
+    cnt = correct_cnt = 0
+
+    def flush(entries, tensors=None, u8=None):
+        nonlocal cnt, correct_cnt
+        if not entries:
+            return
+        if u8 is not None:
+            import numpy as np
+            batch = torch.from_numpy(np.stack(u8))
+            results = predict_batch_u8(model, batch, mean, std, idx_to_class, max_batch_size=batch_size)
+        else:
+            results = predict_batch(model, torch.stack(tensors), idx_to_class, max_batch_size=batch_size)
+        for (name, label, path), (pred, conf) in zip(entries, results):
+            cnt += 1
+            correct_cnt += (pred == label)
+            if out:
+                out.write(f"{name},{pred},{conf:.4f},{label},{pred == label},{path}\n")
+            else:
+                print(f"--- {name}: {pred} (Confidence: {conf:.4f}) Correct: {pred == label}")
+
+    entries, tensors = [], []
+    by_shape = {}
+    for name, label, path in files:
+        try:
+            img = Image.open(path).convert('RGB')
+        except Exception as e:  # same policy as the reference: report and continue
+            print(f"Error processing image {name}: {e}")
+            continue
+        if transforms is None:
+            import numpy as np
+            arr = np.asarray(img, dtype=np.uint8)
+            key = arr.shape[:2]
+            ents, arrs = by_shape.setdefault(key, ([], []))
+            ents.append((name, label, path))
+            arrs.append(arr)
+            if len(ents) >= batch_size:
+                flush(ents, u8=arrs)
+                by_shape[key] = ([], [])
+        else:
+            entries.append((name, label, path))
+            tensors.append(transforms(img))
+            if len(entries) >= batch_size:
+                flush(entries, tensors=tensors)
+                entries, tensors = [], []
+    flush(entries, tensors=tensors)
+    for ents, arrs in by_shape.values():
+        flush(ents, u8=arrs)
+    if out:
+        out.close()
+    if cnt == 0:
+        print("Total images processed: 0")
+        return 0.0
+    print(f"Total images processed: {cnt}, Correct predictions: {correct_cnt}, Accuracy: {correct_cnt / cnt * 100:.2f}%")
+    return correct_cnt / cnt
+
+
+def filter_csv(csv_file: str, output_directory: str):
+    """``filter.filter`` (TIC/utils/filter.py:17-27): copy every correctly predicted picture of a full_judge CSV into
+    ``output_directory/<class>/``. Returns (total rows, copied)."""
+    import csv
+    import shutil
+    tot = cnt = 0
+    with open(csv_file, 'r') as f:
+        for row in csv.DictReader(f):
+            tot += 1
+            if row['predicted_class'].strip() == row['actual_class'].strip():
+                cnt += 1
+                dst = os.path.join(output_directory, row['actual_class'].strip(), os.path.basename(row['path'].strip()))
+                os.makedirs(os.path.dirname(dst), exist_ok=True)
+                shutil.copy(row['path'].strip(), dst)
+    print(f"Tot:{tot}, Copy cnt:{cnt}, Rate:{cnt / tot if tot else 0.0}")
+    return tot, cnt
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Web daemon adapter (web/runtime.py:34-128,235-251) [section 8f rank 3]
+# ----------------------------------------------------------------------------------------------------------------------
+class BatchingPredictor:
+    """Dynamic batching across concurrent callers: requests from any number of threads are queued, one worker thread
+    drains up to ``max_batch_size`` items per forward and hands every caller its own slice back. ``forward`` maps a
+    list of items to a list of results (e.g. a closure over ``predict_batch``)."""
+
+    def __init__(self, forward: Callable[[List], List], max_batch_size: int = 64, max_wait_s: float = 0.002):
+        self.forward, self.max_batch_size, self.max_wait_s = forward, max_batch_size, max_wait_s
+        self._q: "queue.Queue" = queue.Queue()
+        self._stop = threading.Event()
+        self.batches = []  # sizes of the forwards issued so far (observability / tests)
+        self._worker = threading.Thread(target=self._run, daemon=True)
+        self._worker.start()
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                first = self._q.get(timeout=0.05)
+            except queue.Empty:
+                continue
+            pending = [first]
+            n = len(first[0])
+            while n < self.max_batch_size:
+                try:
+                    nxt = self._q.get(timeout=self.max_wait_s)
+                except queue.Empty:
+                    break
+                pending.append(nxt)
+                n += len(nxt[0])
+            items = [it for req in pending for it in req[0]]
+            try:
+                results = []
+                for i in range(0, len(items), self.max_batch_size):
+                    chunk = items[i:i + self.max_batch_size]
+                    self.batches.append(len(chunk))
+                    results.extend(self.forward(chunk))
+                err = None
+            except Exception as e:  # hand the failure to every waiting caller
+                results, err = None, e
+            off = 0
+            for req_items, box, done in pending:
+                box.append(err if err is not None else results[off:off + len(req_items)])
+                off += len(req_items)
+                done.set()
+
+    def __call__(self, items: List) -> List:
+        box, done = [], threading.Event()
+        self._q.put((list(items), box, done))
+        done.wait()
+        if isinstance(box[0], Exception):
+            raise box[0]
+        return box[0]
+
+    def close(self):
+        self._stop.set()
+        self._worker.join(timeout=1.0)
+
+
+class ModelDaemon:
+    """Drop-in for ``web/runtime.py:ModelDaemon`` (``predict`` on a PIL image or a list of them -> (class, confidence)
+    or a list of pairs), with the forward on the engine and concurrent requests coalesced into shared batches.
+    ``transforms`` is the reference's CPU transform (``get_transforms``); pass ``mean`` / ``std`` instead to run the
+    resize + normalise on the GPU for same-sized pictures."""
+
+    MAX_BATCH_SIZE = 64
+
+    def __init__(self, model, class_to_idx, transforms=None, mean=None, std=None, max_batch_size: int = None):
+        if transforms is None and (mean is None or std is None):
+            raise ValueError("ModelDaemon needs either the reference's transforms or the dataset mean / std")
+        self.model = model.eval()
+        self.class_to_idx = class_to_idx
+        self.idx_to_class = {v: k for k, v in class_to_idx.items()}
+        self.transforms, self.mean, self.std = transforms, mean, std
+        self.lock = threading.Lock()
+        self._batcher = BatchingPredictor(self._forward, max_batch_size or self.MAX_BATCH_SIZE)
+
+    def _forward(self, images):
+        if self.transforms is not None:
+            batch = torch.stack([self.transforms(im) for im in images])
+            return predict_batch(self.model, batch, self.idx_to_class, max_batch_size=len(images))
+        import numpy as np
+        arrs = [np.asarray(im, dtype=np.uint8) for im in images]
+        out = [None] * len(arrs)
+        groups = {}
+        for i, a in enumerate(arrs):
+            groups.setdefault(a.shape[:2], []).append(i)
+        for idxs in groups.values():
+            res = predict_batch_u8(self.model, torch.from_numpy(np.stack([arrs[i] for i in idxs])), self.mean, self.std,
+                                   self.idx_to_class, max_batch_size=len(idxs))
+            for i, r in zip(idxs, res):
+                out[i] = r
+        return out
+
+    def predict(self, images):
+        is_single = not isinstance(images, list)
+        if is_single:
+            images = [images]
+        images = [im.convert('RGB') if getattr(im, 'mode', 'RGB') != 'RGB' else im for im in images]
+        results = self._batcher(images)
+        return results[0] if is_single else results
+
+    def stop(self):
+        self._batcher.close()
