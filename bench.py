@@ -208,7 +208,7 @@ def run_ours(args):
     torch.manual_seed(1234)
     model = ViTForImageClassification(ViTConfig(**WORKLOAD)).to(dev).train()
     opt = FusedAdamW(model, lr=1e-5, weight_decay=0.01)
-    trainer = DataParallelTrainer(model, opt)
+    trainer = DataParallelTrainer(model, opt, bucket_mb=args.bucket_mb)
     trainer.broadcast_parameters(0)
     B, S = PER_GPU_BATCH, WORKLOAD["image_size"]
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
@@ -378,6 +378,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--bucket-mb", type=float, default=96.0, help="gradient all-reduce bucket size (N > 1)")
     ap.add_argument("--no-inference", action="store_true", help="skip the batched-inference sweep after the training bench")
     args = ap.parse_args()
     if args.impl == "reference":
