@@ -275,3 +275,26 @@ def test_cutmix_mixup_kernel_is_bit_exact_against_torchvision_restatement():
         assert torch.equal(po, ops.patchify_f32(xr.to(dev))), seed
         seen.add(bool((xr != x).any() and (xr == x).any()))
     assert seen == {True, False} or len(seen) == 2 or True
+
+
+def test_small_batch_inference_graph_matches_eager_and_tracks_weight_updates():
+    """Batches <= graph_max_batch replay a captured CUDA graph: same logits as the eager launch sequence, still correct
+    after the weights change in place, after a different batch size, and after the model moved (.to())."""
+    m = make(TINY, 0.05).eval()
+    x = O.deterministic_images(3, 32, seed=1).to(dev)
+    with torch.no_grad():
+        m.graph_max_batch = 0
+        eager = m(x).logits.clone()
+        m.graph_max_batch = 64
+        g1 = m(x).logits.clone()
+        g2 = m(x).logits.clone()
+        assert torch.equal(g1, eager) and torch.equal(g2, eager) and 3 in m._graphs
+        x5 = O.deterministic_images(5, 32, seed=2).to(dev)
+        m.graph_max_batch = 0
+        e5 = m(x5).logits.clone()
+        m.graph_max_batch = 64
+        assert torch.equal(m(x5).logits, e5) and torch.equal(m(x).logits, eager)
+        m.classifier.bias.add_(0.25)                       # in-place weight update: the shadow is refreshed outside the graph
+        assert torch.allclose(m(x).logits, eager + 0.25, atol=2e-2)
+        m.to("cpu"); m.to(dev)                             # new arena -> the graph is rebuilt
+        assert torch.allclose(m(x).logits, eager + 0.25, atol=2e-2)

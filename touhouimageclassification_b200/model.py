@@ -195,6 +195,9 @@ class ViTForImageClassification(nn.Module):
         self.precision = "bf16"
         self._w6 = None
         self._w6_key = None
+        # CUDA graphs of the inference forward for small batches (the web / serve path is launch-bound at batch 1-64)
+        self.graph_max_batch = 64
+        self._graphs = {}
 
     # ---- structure ------------------------------------------------------------------------------
     def _build_tree(self, params):
@@ -276,6 +279,7 @@ class ViTForImageClassification(nn.Module):
         self._w6_key = None
         self._grad_arena = None
         self._workspaces = {}
+        self._graphs = {}
 
     def _apply(self, fn, recurse=True):
         super()._apply(fn, recurse)
@@ -426,6 +430,8 @@ class ViTForImageClassification(nn.Module):
                 assert patches.dtype == torch.bfloat16 and patches.is_cuda and patches.is_contiguous()
                 batch = patches.shape[0] // P
                 x = None
+            if not training and x is not None and batch <= self.graph_max_batch and not torch.cuda.is_current_stream_capturing():
+                return self._graph_forward(x, batch)
             ws = self._workspace(batch, training)
             if training:
                 self._ws_generation += 1
@@ -437,6 +443,38 @@ class ViTForImageClassification(nn.Module):
                 c_int(batch), c_void_p(ws.data_ptr()), c_i64(ws.numel()), c_int(int(training)),
                 c_void_p(logits.data_ptr()), _stream()))
             return logits
+
+    def _graph_forward(self, x: torch.Tensor, batch: int) -> torch.Tensor:
+        """Inference forward of a small batch as ONE CUDA-graph launch: the ~220 kernel launches (and their tensor-map
+        encodes) of a ViT-L forward cost more host time than device time below batch 64. The graph is captured once per
+        batch size over static input / logits / workspace buffers; weights are read through the (stable) shadow arena,
+        which refresh_shadow() keeps current outside the graph."""
+        entry = self._graphs.get(batch)
+        if entry is None or entry["shadow_ptr"] != self._shadow.data_ptr() or entry["arena_ptr"] != self._arena.data_ptr():
+            dev = self._arena.device
+            ws = self._workspace(batch, False)
+            xin = torch.empty_like(x)
+            out = torch.empty((batch, self.config.num_labels), dtype=torch.float32, device=dev)
+            c = self.config.to_c()
+
+            def launch():
+                _lib.check(_lib.load().tic_vit_forward(
+                    ctypes.byref(c), c_void_p(self._arena.data_ptr()), c_void_p(self._shadow.data_ptr()),
+                    c_void_p(xin.data_ptr()), c_void_p(0), c_int(batch), c_void_p(ws.data_ptr()), c_i64(ws.numel()),
+                    c_int(0), c_void_p(out.data_ptr()), _stream()))
+
+            xin.copy_(x)
+            launch()  # eager warm-up: one-time function attributes and driver entry points are set outside the capture
+            torch.cuda.current_stream().synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                launch()
+            entry = dict(graph=graph, x=xin, out=out, ws=ws, shadow_ptr=self._shadow.data_ptr(),
+                         arena_ptr=self._arena.data_ptr())
+            self._graphs[batch] = entry
+        entry["x"].copy_(x)
+        entry["graph"].replay()
+        return entry["out"].clone()
 
     def engine_backward(self, dlogits: torch.Tensor, batch: int, head_only: bool = False, stage_begin: int = 0,
                         stage_end: Optional[int] = None):
