@@ -25,6 +25,17 @@ if ROOT not in sys.path:
 WORKLOAD = dict(hidden_size=1024, num_hidden_layers=24, num_attention_heads=16, intermediate_size=4096,
                 image_size=224, num_labels=120)
 PER_GPU_BATCH = 256
+METRIC = "vit_l16_224_train_images_per_sec"
+WORKLOAD_NAME = "ViT-L/16 224x224"
+# The headline (BASELINE.json metric) is the default; the other BASELINE configs can be measured with --workload.
+WORKLOADS = {
+    "vitl224": (dict(hidden_size=1024, num_hidden_layers=24, num_attention_heads=16, intermediate_size=4096, image_size=224,
+                     num_labels=120), 256, "vit_l16_224_train_images_per_sec", "ViT-L/16 224x224"),
+    "vitb224": (dict(hidden_size=768, num_hidden_layers=12, num_attention_heads=12, intermediate_size=3072, image_size=224,
+                     num_labels=120), 256, "vit_b16_224_train_images_per_sec", "ViT-B/16 224x224"),
+    "vitl384": (dict(hidden_size=1024, num_hidden_layers=24, num_attention_heads=16, intermediate_size=4096, image_size=384,
+                     num_labels=120), 128, "vit_l16_384_train_images_per_sec", "ViT-L/16 384x384"),
+}
 
 
 def flops_per_image_forward(c):
@@ -151,7 +162,7 @@ def cpu_train_steps(steps, warmup, time_budget_s, batch=8):
     times = [one(batch) for _ in range(steps)]
     ms = statistics.median(times) * 1e3
     sample = (f"{what} fp32 train step (zero_grad, forward, CrossEntropyLoss, backward, AdamW lr 1e-5 wd 0.01, loss.item) "
-              f"on ViT-L/16 224x224, batch {batch} per step, {steps} timed steps after {warmup} warm-up, median; "
+              f"on {WORKLOAD_NAME}, batch {batch} per step, {steps} timed steps after {warmup} warm-up, median; "
               f"{cores} host threads")
     return batch / (ms / 1e3), ms, kind, cores, sample
 
@@ -170,13 +181,14 @@ def run_reference(args):
 
 
 def base_line(args, n_gpus):
-    return dict(metric="vit_l16_224_train_images_per_sec", value=None, unit="img/s", n_gpus=n_gpus, steps=args.steps,
+    return dict(metric=METRIC, value=None, unit="img/s", n_gpus=n_gpus, steps=args.steps,
                 warmup=args.warmup, ms_per_step=None, higher_is_better=True, scaling="weak", vs_baseline=None,
                 dtype="bf16", data="synthetic",
-                config=dict(workload="ViT-L/16 224x224 bf16 fine-tune step (forward, softmax-CE, backward, AdamW), "
+                config=dict(workload=WORKLOAD_NAME + " bf16 fine-tune step (forward, softmax-CE, backward, AdamW), "
                                      "random-init weights, synthetic N(0,1) images, int labels",
-                            per_gpu_batch=PER_GPU_BATCH, global_batch=PER_GPU_BATCH * n_gpus, tokens=197,
-                            parallelism=f"dp{n_gpus}", l2_policy="inputs_exceed_l2 (46 GB of activations per step)"))
+                            per_gpu_batch=PER_GPU_BATCH, global_batch=PER_GPU_BATCH * n_gpus,
+                            tokens=(WORKLOAD["image_size"] // 16) ** 2 + 1,
+                            parallelism=f"dp{n_gpus}", l2_policy="inputs_exceed_l2 (tens of GB of activations per step)"))
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -310,7 +322,7 @@ def run_ours(args):
         torch.cuda.empty_cache()
         model.eval()
         fwd_flops = flops_per_image_forward(WORKLOAD)
-        inference = dict(unit="img/s", dtype="bf16", note="ViT-L/16 224x224 forward (engine_forward), inputs resident in HBM, "
+        inference = dict(unit="img/s", dtype="bf16", note=WORKLOAD_NAME + " forward (engine_forward), inputs resident in HBM, "
                          "CUDA events, per GPU replica", batches={})
 
         def time_forward(fn, iters):
@@ -326,7 +338,7 @@ def run_ours(args):
             return a.elapsed_time(b2) / iters
 
         with torch.no_grad():
-            for bs in (1, 8, 64, 256, 1024):
+            for bs in ((1, 8, 64, 256, 1024) if WORKLOAD["image_size"] <= 224 else (1, 8, 64, 256)):
                 xb = torch.randn(bs, 3, S, S, device=dev, generator=g)
                 ms = time_forward(lambda: model.engine_forward(xb, training=False), 20 if bs <= 64 else 5)
                 ips = bs / (ms / 1e3)
@@ -380,7 +392,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--bucket-mb", type=float, default=96.0, help="gradient all-reduce bucket size (N > 1)")
     ap.add_argument("--no-inference", action="store_true", help="skip the batched-inference sweep after the training bench")
+    ap.add_argument("--workload", default="vitl224", choices=sorted(WORKLOADS),
+                    help="vitl224 = the BASELINE.json headline (default); vitb224 / vitl384 = BASELINE configs 2 and 5")
     args = ap.parse_args()
+    global WORKLOAD, PER_GPU_BATCH, METRIC, WORKLOAD_NAME
+    WORKLOAD, PER_GPU_BATCH, METRIC, WORKLOAD_NAME = WORKLOADS[args.workload]
     if args.impl == "reference":
         run_reference(args)
     else:
