@@ -32,22 +32,25 @@ constexpr int BK = 64;
 constexpr int UMMA_K = 16;
 constexpr int ACC_STAGES = 2;
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
-constexpr int NUM_EPI_WARPS = 8;
-constexpr int NUM_THREADS = (NUM_EPI_WARPS + 2) * 32;
+// Epilogue warps per CTA: 8 (two per TMEM lane quadrant) everywhere except the GELU forward epilogue, whose ~24
+// instructions per element (value + derivative) need more issue slots than two warps per SM sub-partition deliver inside
+// one tile's MMA time: it runs 12 (three per quadrant, column chunks dealt round-robin) and gives up one operand stage.
+template <int EPI>
+constexpr int epi_warps() { return EPI == kEpiBf16Gelu ? 12 : 8; }
 constexpr int TMEM_COLS = ACC_STAGES * BN;  // 512
 constexpr int EPI_STAGE_BYTES = 32 * 32 * 4;  // per epilogue warp: 32 rows x 32 fp32 columns
 
 // NCTA = 1: one CTA computes a 128 x 256 tile.  NCTA = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) computes a
 // 256 x 256 tile with one UMMA M=256: each CTA stages its own 128 A rows and HALF of the B tile (128 of the 256
 // N rows), which halves the L2 -> smem operand traffic per FLOP and frees smem for a deeper ring.
-template <int NCTA>
+template <int NCTA, int NEPI = 8>
 struct Cfg {
   static constexpr int B_ROWS = BN / NCTA;                 // B rows (N) staged per CTA
   static constexpr int B_STAGE_BYTES = B_ROWS * BK * 2;    // 32 KB / 16 KB
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES = NCTA == 2 ? 6 : 4;
+  static constexpr int STAGES = NCTA == 2 ? (NEPI > 8 ? 5 : 6) : 4;
   static constexpr int TILE_M = BM * NCTA;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + NUM_EPI_WARPS * EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + NEPI * EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
 
@@ -67,10 +70,13 @@ struct GemmParams {
 };
 
 template <bool A_MN, bool B_MN, int EPI, int NCTA>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__((epi_warps<EPI>() + 2) * 32, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const GemmParams p) {
-  using C = Cfg<NCTA>;
+  constexpr int NUM_EPI_WARPS = epi_warps<EPI>();
+  constexpr int kTmaWarp = NUM_EPI_WARPS, kMmaWarp = NUM_EPI_WARPS + 1;
+  constexpr int kParts = NUM_EPI_WARPS / 4;  // epilogue warps per TMEM lane quadrant
+  using C = Cfg<NCTA, NUM_EPI_WARPS>;
   constexpr int STAGES = C::STAGES;
   constexpr int B_STAGE_BYTES = C::B_STAGE_BYTES;
   constexpr int STAGE_BYTES = C::STAGE_BYTES;
@@ -100,12 +106,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   const int tiles_per_split = m_blocks * n_blocks;
   const int total_tiles = tiles_per_split * p.splits;
 
-  if (warp == 8 && lane == 0) {
+  if (warp == kTmaWarp && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
   }
   if constexpr (NCTA == 2) cluster_sync_all();  // both CTAs are resident before the paired TMEM allocation
-  if (warp == 9) {
+  if (warp == kMmaWarp) {
     if (lane == 0) {
       for (int i = 0; i < STAGES; ++i) {
         mbar_init(&full_bar[i], NCTA);   // the leader's barrier collects one producer arrival per CTA
@@ -127,7 +133,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
 
-  if (warp == 8) {
+  if (warp == kTmaWarp) {
     // ------------------------------------------------------------------ TMA producer
     if (elect_one()) {
       int stage = 0;
@@ -168,7 +174,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == kMmaWarp) {
     // ------------------------------------------------------------------ MMA issuer
     if (cta_rank == 0 && elect_one()) {
       constexpr uint32_t idesc = make_idesc_bf16(C::TILE_M, BN, A_MN, B_MN);
@@ -219,7 +225,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     //          all epilogue math and every global access (bias, residual, pre-activation, outputs) happens
     //          here with fully coalesced 128-bit (fp32) / 64-bit (bf16) accesses.
     const int quad = warp & 3;   // TMEM lane quadrant this warp may access
-    const int half = warp >> 2;  // which 128-column half of the accumulator
+    const int part = warp >> 2;  // this warp takes the 32-column chunks part, part + kParts, ... of the accumulator
     uint8_t* stg = smem_stage + warp * EPI_STAGE_BYTES;
     const int sub_row = lane >> 3;  // phase B: row within a group of 4
     const int ch = lane & 7;        // phase B: 16-byte chunk (4 fp32 columns)
@@ -234,8 +240,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       tc_fence_after();
       const int row_base = m_idx + quad * 32;
 #pragma unroll 1
-      for (int c = 0; c < BN / 2 / 32; ++c) {
-        const int col0 = n_idx + half * (BN / 2) + c * 32;
+      for (int c = part; c < BN / 32; c += kParts) {
+        const int col0 = n_idx + c * 32;
         const int col = col0 + ch * 4;
         // Issue this chunk's coalesced auxiliary loads (residual / pre-activation / pos-emb rows) before the
         // TMEM load so that their latency overlaps phase A.
@@ -262,7 +268,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         }
         {
           uint32_t r[32];
-          const uint32_t taddr = tmem_base + acc_stage * BN + half * (BN / 2) + c * 32 + (static_cast<uint32_t>(quad * 32) << 16);
+          const uint32_t taddr = tmem_base + acc_stage * BN + c * 32 + (static_cast<uint32_t>(quad * 32) << 16);
           tmem_ld_32x32b_x32(taddr, r);
           tmem_ld_wait();
           const uint32_t stg_wr = smem_u32(stg) + lane * 128;
@@ -397,7 +403,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   if constexpr (NCTA == 2) cluster_sync_all();  // remote arrivals and the peer's smem reads have all landed
   else __syncthreads();
   tc_fence_after();
-  if (warp == 9) {
+  if (warp == kMmaWarp) {
     if constexpr (NCTA == 2) tmem_dealloc_2cta(tmem_base, TMEM_COLS);
     else tmem_dealloc(tmem_base, TMEM_COLS);
   }
@@ -419,7 +425,7 @@ constexpr int kNcta = 2;  // CTA pairs (tcgen05 cta_group::2)
 
 template <bool A_MN, bool B_MN, int EPI>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
-  using C = Cfg<kNcta>;
+  using C = Cfg<kNcta, epi_warps<EPI>()>;
   auto kern = gemm_bf16_tcgen05_kernel<A_MN, B_MN, EPI, kNcta>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -433,7 +439,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cu
   const int workers = total < max_workers ? total : max_workers;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(workers * kNcta);
-  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.blockDim = dim3((epi_warps<EPI>() + 2) * 32);
   cfg.dynamicSmemBytes = C::SMEM_BYTES;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
