@@ -14,12 +14,13 @@
 //                            with M = 128 queries, K = 128 keys; issued once per pair of query blocks)
 //   warps 0-7          one key row per thread, two warps per TMEM lane quadrant (32 query columns each):
 //        P^T = exp2(S^T c - L[q]),  dS^T = P^T o (dP^T - delta[q]);  packed bf16 back into TMEM (in place) and into
-//        the smem staging tile; drains dV / dK after each key tile and dQ at the end.
+//        the smem staging tile.
+//   warps 9-12         drain warps, one per lane quadrant: dV / dK after each key tile and dQ at the end leave TMEM
+//        through registers -> per-warp smem tiles -> TMA stores, off the compute warps' critical path; the MMA thread
+//        only waits for the (fast) TMEM reads before it overwrites an accumulator.
 // S / dP are double buffered in TMEM so the score MMAs of block j+1 run under the elementwise pass of block j.
 // delta[q] = rowsum(dO o O) comes from shared memory: O is TMA-loaded into the (still unused) second staging tile and
 // each compute thread dots its own row of O and dO; no separate delta kernel, no global loads on the critical path.
-// The drain of a key tile's dV / dK is deferred until after the elementwise pass of the NEXT block, so the wait for
-// that tile's last MMAs is hidden behind useful work.
 // TMEM (512 columns): S[2] 0-127 | dP[2] 128-255 | dV 256-319 | dK 320-383 | dQ[2 query tiles] 384-511.
 #include "tic_internal.cuh"
 
@@ -28,14 +29,18 @@
 namespace tic {
 namespace {
 
-constexpr int FB_THREADS = 288;  // 8 compute warps + 1 TMA / MMA warp
+constexpr int FB_THREADS = 512;  // 8 compute warps + 1 TMA / MMA warp + 4 drain warps (one per TMEM lane quadrant) + 3 idle
+// Register budget: warps are allocated in groups of four, so 13 warps cost 16 x 32 x regs. The kernel is compiled for
+// 128 registers per thread and re-balances at run time (setmaxnreg): the two compute warpgroups grow to 168, the MMA /
+// drain warpgroups shrink to 88 -- 8 x 32 x (168 + 88) = the whole register file.
+constexpr int FB_REGS_COMPUTE = 168, FB_REGS_OTHER = 88;
 constexpr int FB_ROWS = 256;     // rows staged per operand
 constexpr int FB_HD = 64;
 constexpr float FB_LOG2E = 1.4426950408889634f;
 constexpr int FB_OPER_BYTES = FB_ROWS * 128;   // 32 KB per operand
 constexpr int FB_STAGE_BYTES = 2 * 128 * 128;  // one dS^T tile: 2 query chunks x 128 key rows x 128 B
-constexpr int FB_OUT_BYTES = 8 * 2 * 2048;       // per compute warp: two 32-row x 64-byte output tiles for the TMA stores
-constexpr int FB_SMEM_USED = 4 * FB_OPER_BYTES + 2 * FB_STAGE_BYTES + FB_OUT_BYTES + 2 * FB_ROWS * 4 + 64;
+constexpr int FB_OUT_BYTES = 4 * 4 * 2048;       // per drain warp: four 32-row x 64-byte output tiles for the TMA stores
+constexpr int FB_SMEM_USED = 4 * FB_OPER_BYTES + 2 * FB_STAGE_BYTES + FB_OUT_BYTES + 2 * FB_ROWS * 4 + 128;
 constexpr int FB_SMEM = 232448;                  // everything the SM has; the slack (960 B) absorbs the 1024-byte alignment
 static_assert(FB_SMEM_USED <= FB_SMEM, "attention_bwd_fused: shared memory budget");
 constexpr uint32_t FB_COL_DP = 128, FB_COL_DV = 256, FB_COL_DK = 320, FB_COL_DQ = 384;
@@ -79,7 +84,7 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
                       const float* __restrict__ lse, float* __restrict__ bias_grad, int bias_mask, int N, int H, int num_items, float scale,
                       long long* __restrict__ trace) {
   // trace (dev tool, normally NULL): clock64 stamps of CTA 0 -- [0..63] compute warp 0, [64..127] the MMA thread
-#define FB_STAMP(slot) do { if (trace != nullptr && blockIdx.x == 0 && it == 1) trace[slot] = clock64(); } while (0)
+#define FB_STAMP(slot) do { if (trace != nullptr && blockIdx.x == 0 && it == 3) trace[slot] = clock64(); } while (0)
   extern __shared__ uint8_t fb_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(fb_smem_raw) + 1023) & ~uintptr_t(1023));
   if (smem + FB_SMEM_USED > fb_smem_raw + FB_SMEM) {  // never observed: the dynamic window starts 1024-byte aligned
@@ -98,8 +103,10 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
   uint64_t* bar_load = bars + 0;  // [2] K + Q  |  dO + O + V
   uint64_t* bar_s = bars + 2;    // [2] score tiles of a block are in TMEM
   uint64_t* bar_p = bars + 4;    // [2] P^T / dS^T of a block written (8 warp arrivals)
-  uint64_t* bar_acc = bars + 6;  // every MMA of a key tile has completed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
+  uint64_t* bar_acc = bars + 6;      // every MMA of a key tile has completed
+  uint64_t* bar_free_vk = bars + 7;  // the drain warps have read dV / dK of a key tile out of TMEM (4 warp arrivals)
+  uint64_t* bar_free_q = bars + 8;   // ... and dQ of an item
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
   uint8_t* sO = sStage + FB_STAGE_BYTES;  // O rows live in the second staging tile until delta has been computed
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -119,6 +126,8 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       mbar_init(&bar_p[0], 8);
       mbar_init(&bar_p[1], 8);
       mbar_init(bar_acc, 1);
+      mbar_init(bar_free_vk, 4);
+      mbar_init(bar_free_q, 4);
       fence_mbar_init();
     }
     __syncwarp();
@@ -128,6 +137,8 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (warp < 8) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(FB_REGS_COMPUTE));
+  else asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(FB_REGS_OTHER));
 
   // Persistent: this CTA walks the (image, head) items blockIdx.x, blockIdx.x + gridDim.x, ... The loads of item i+1
   // are issued as soon as the last MMA of item i has completed, i.e. under the final accumulator drain of item i.
@@ -147,7 +158,7 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         tma_load_3d(sO, &tm_o, &bar_load[1], h * FB_HD, 0, b);
         tma_load_3d(sV, &tm_v, &bar_load[1], h * FB_HD, 0, b);
       };
-      uint32_t ph_p = 0, use_acc = 0;  // ph_p: bit b = parity of the next completion of bar_p[b]
+      uint32_t ph_p = 0, use_acc = 0, use_vk = 0;  // ph_p: bit b = parity of the next completion of bar_p[b]
       issue_loads(blockIdx.x);
       for (int it = 0, item = blockIdx.x; item < num_items; ++it, item += gridDim.x) {
         auto issue_scores = [&](int j) {
@@ -176,6 +187,11 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
           FB_STAMP(70 + 2 * j);
           ph_p ^= 1u << buf;
           tc_fence_after();
+          if (qb == 0 && (it > 0 || kt > 0)) {  // the previous key tile's dV / dK have left TMEM
+            mbar_wait(bar_free_vk, use_vk & 1);
+            ++use_vk;
+            tc_fence_after();
+          }
           const int ksteps = (qb == nqb - 1 ? w_last : 64) >> 4;
           const uint64_t dO_mn = make_smem_desc_sw128(aDO + qb * 8192, 8192, 1024);
           const uint64_t dQ_mn = make_smem_desc_sw128(aQ + qb * 8192, 8192, 1024);
@@ -187,11 +203,19 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
             const uint32_t a = tmem_base + FB_COL_DP + buf * 64 + (k >> 1) * 32 + (k & 1) * 8;
             umma_bf16_ts(tmem_base + FB_COL_DK, a, dQ_mn + 128 * k, idesc_ts, (qb > 0 || k > 0) ? 1u : 0u);
           }
+          // dV / dK of a key tile that is not the last one are complete here: let the drain warps start before the score
+          // and dQ products queued behind them
+          const bool tile_end = qb == nqb - 1, early = tile_end && kt < nkt - 1;
+          if (early) umma_commit(bar_acc);
           // the P^T / dS^T columns of this buffer have been consumed (in issue order): refill it with the scores of
           // block j+2 before the dQ product, which the compute warps do not wait for
           if (j + 2 < J) issue_scores(j + 2);
           if ((qb & 1) || qb == nqb - 1) {    // dQ[query tile] += dS K over this key tile
             const int qt = qb >> 1;
+            if (kt == 0 && qt == 0 && it > 0) {  // the previous item's dQ has left TMEM
+              mbar_wait(bar_free_q, (it - 1) & 1);
+              tc_fence_after();
+            }
             const int kvalid = min(128, N - kt * 128);
             const int ks = (kvalid + 15) >> 4;
             const uint64_t dS_mn = make_smem_desc_sw128(aS + qt * FB_STAGE_BYTES, 16384, 1024);
@@ -200,8 +224,8 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
               umma_bf16_ss(tmem_base + FB_COL_DQ + qt * 64, dS_mn + 128 * k, dK_mn + 128 * k, idesc_dq, (kt > 0 || k > 0) ? 1u : 0u);
           }
           FB_STAMP(71 + 2 * j);
-          if (qb == nqb - 1) {
-            umma_commit(bar_acc);
+          if (tile_end) {
+            if (!early) umma_commit(bar_acc);
             if (kt == nkt - 1 && item + static_cast<int>(gridDim.x) < num_items) {
               // every MMA of this item has read its operands: refill the operand buffers for the next item
               mbar_wait(bar_acc, use_acc & 1);
@@ -215,7 +239,7 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       }
     }
     __syncwarp();
-  } else {
+  } else if (warp < 8) {
     // ------------------------------------------------------------------------------------ compute warps
     const int quad = warp & 3, half = warp >> 2;
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
@@ -225,10 +249,8 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     const int sw = r & 7;
     const int t = threadIdx.x;       // 0..255: the query whose delta / logsumexp this thread prepares
     const uint32_t aL = smem_u32(sL), aD = smem_u32(sD);
-    const uint32_t out_tile = smem_u32(sOut) + warp * 4096;
-    uint32_t out_sel = 0;
     const uint32_t ro = smem_u32(sO) + t * 128, rd = smem_u32(sDO) + t * 128;
-    uint32_t ph_s = 0, use_acc = 0;  // ph_s: bit b = parity of the next completion of bar_s[b]
+    uint32_t ph_s = 0;  // bit b = parity of the next completion of bar_s[b]
     auto load_lse = [&](int item) -> float {  // per-query logsumexp, +inf past N: exp2(-inf) = 0
       return (item < num_items && t < N) ? __ldg(lse + static_cast<long long>(item) * N + t) : INFINITY;
     };
@@ -256,59 +278,6 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         asm volatile("bar.sync 1, 256;" ::: "memory");
         FB_CSTAMP(2);
       }
-      auto colsum_to = [&](const uint32_t (&pk)[16], bool valid, float* dst) {
-        float v[32];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          v[2 * i] = valid ? bf16_lo(pk[i]) : 0.f;
-          v[2 * i + 1] = valid ? bf16_hi(pk[i]) : 0.f;
-        }
-        const float cs = warp_colsum32(v, lane);
-        atomicAdd(dst + h * FB_HD + half * 32 + lane, cs);
-      };
-      // This warp's 32 x 32 bf16 output tile -> one of its two private staging tiles -> one TMA store (rows past N are
-      // clipped by the tensor map). Direct 16-byte stores at a 6 KB row pitch cost ~300 clk per instruction and stalled
-      // the drain.
-      auto store_tile = [&](const CUtensorMap* tm, const uint32_t (&pk)[16], int row0) {
-        if (lane == 0) tma_store_wait_read<1>();  // the store before the previous one has finished reading this tile
-        __syncwarp();
-        out_sel ^= 1u;
-        const uint32_t region = out_tile + out_sel * 2048;
-        const uint32_t base = region + lane * 64;
-        const int x = (lane >> 1) & 3;
-#pragma unroll
-        for (int pc = 0; pc < 4; ++pc)
-          st_shared_v4(base + ((pc ^ x) << 4), pk[4 * pc], pk[4 * pc + 1], pk[4 * pc + 2], pk[4 * pc + 3]);
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) {
-          tma_store_3d_addr(tm, region, h * FB_HD + half * 32, row0, b);
-          tma_store_commit();
-        }
-      };
-      int pending_kt = -1;  // key tile whose dV / dK still have to be drained
-      auto drain_kt = [&](int kt) {
-        const bool quad_active = kt * 128 + quad * 32 < N;
-        mbar_wait(bar_acc, use_acc & 1);
-        ++use_acc;
-        tc_fence_after();
-        const int row = kt * 128 + r;
-#pragma unroll 1
-        for (int a = 0; a < 2; ++a) {  // a = 0: dV (unscaled), a = 1: dK (* scale)
-          if (!quad_active) break;
-          const float f = a == 0 ? 1.0f : scale;
-          uint32_t rr[32];
-          tmem_ld_32x32b_x32(lane_addr + (a == 0 ? FB_COL_DV : FB_COL_DK) + half * 32, rr);
-          tmem_ld_wait();
-          uint32_t pk[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(__uint_as_float(rr[2 * i]) * f, __uint_as_float(rr[2 * i + 1]) * f);
-          store_tile(a == 0 ? &tm_dv : &tm_dk, pk, kt * 128 + quad * 32);
-          // column sums of the bf16 gradient rows = bias gradient of the fused QKV Linear (k: bit 1, v: bit 2)
-          if (bias_mask & (a == 0 ? 4 : 2)) colsum_to(pk, row < N, bias_grad + (a == 0 ? 2 : 1) * H * FB_HD);
-        }
-        tc_fence_before();
-      };
       for (int j = 0; j < J; ++j) {
         const int kt = j >= nqb ? 1 : 0, qb = j - kt * nqb, buf = j & 1;
         const int w = qb == nqb - 1 ? w_last : 64;
@@ -352,44 +321,113 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
           fence_proxy_async();
         }
         FB_CSTAMP(5 + 3 * j);
-        if (pending_kt >= 0) {  // the previous key tile's accumulators must be read before this block's TS MMAs overwrite them
-          drain_kt(pending_kt);
-          pending_kt = -1;
-        }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar_p[buf]);
         FB_CSTAMP(6 + 3 * j);
 
-        if (qb == nqb - 1) {
-          if (kt < nkt - 1) {
-            pending_kt = kt;  // drained after the next block's elementwise pass
-          } else {
-            L_next = load_lse(item + gridDim.x);  // in flight during the final drain
-            drain_kt(kt);
-            FB_CSTAMP(40);
-            tc_fence_after();
-            for (int qt = 0; qt < nkt; ++qt) {
-              const int qrow = qt * 128 + r;
-              if (qt * 128 + quad * 32 >= N) break;
-              uint32_t rr[32];
-              tmem_ld_32x32b_x32(lane_addr + FB_COL_DQ + qt * 64 + half * 32, rr);
-              tmem_ld_wait();
-              uint32_t pk[16];
+        if (j == J - 1) L_next = load_lse(item + gridDim.x);  // in flight across the item boundary
+      }
+    }
+  }
+  if (warp > 8 && warp < 13) {
+    // ------------------------------------------------------------------------------------ drain warps
+    const int quad = warp & 3;  // warps 9, 10, 11, 12 -> TMEM lane quadrants 1, 2, 3, 0
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    const uint32_t stage = smem_u32(sOut) + (warp - 9) * 8192;  // four 2 KB tiles: [32 rows][64 B], 64-byte swizzle
+    const int r = quad * 32 + lane;
+    uint32_t use_acc = 0;
+    for (int it = 0, item = blockIdx.x; item < num_items; ++it, item += gridDim.x) {
+      const int h = item % H, b = item / H;
+      // One half tile (32 rows x 32 fp32 accumulator columns of this warp's lane quadrant): TMEM -> scaled, packed bf16
+      // -> staging slot (64-byte swizzle); column sums of the bf16 rows accumulate into the QKV bias gradient when asked
+      // for. Done one half tile at a time so that the drain warps live within their 88 registers.
+      auto stage_half = [&](int slot, uint32_t col, float f, bool valid, float* bias_dst, int half) {
+        uint32_t rr[32];
+        tmem_ld_32x32b_x32(lane_addr + col, rr);
+        tmem_ld_wait();
+        uint32_t pk[16];
 #pragma unroll
-              for (int i = 0; i < 16; ++i)
-                pk[i] = pack_bf16x2(__uint_as_float(rr[2 * i]) * scale, __uint_as_float(rr[2 * i + 1]) * scale);
-              store_tile(&tm_dq, pk, qt * 128 + quad * 32);
-              if (bias_mask & 1) colsum_to(pk, qrow < N, bias_grad);
+        for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(__uint_as_float(rr[2 * i]) * f, __uint_as_float(rr[2 * i + 1]) * f);
+        const uint32_t base = stage + slot * 2048 + lane * 64;
+        const int x = (lane >> 1) & 3;
+#pragma unroll
+        for (int pc = 0; pc < 4; ++pc)
+          st_shared_v4(base + ((pc ^ x) << 4), pk[4 * pc], pk[4 * pc + 1], pk[4 * pc + 2], pk[4 * pc + 3]);
+        if (bias_dst != nullptr) {
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            v[2 * i] = valid ? bf16_lo(pk[i]) : 0.f;
+            v[2 * i + 1] = valid ? bf16_hi(pk[i]) : 0.f;
+          }
+          const float cs = warp_colsum32(v, lane);
+          atomicAdd(bias_dst + h * FB_HD + half * 32 + lane, cs);
+        }
+      };
+      for (int kt = 0; kt < nkt; ++kt) {
+        const bool quad_active = kt * 128 + quad * 32 < N;
+        const int row0 = kt * 128 + quad * 32;
+        const bool valid = kt * 128 + r < N;
+        mbar_wait(bar_acc, use_acc & 1);
+        ++use_acc;
+        tc_fence_after();
+        if (lane == 0) tma_store_wait_read<0>();  // this warp's staging slots are free again (stores issued long ago)
+        __syncwarp();
+        if (quad_active) {
+          float* vdst = (bias_mask & 4) ? bias_grad + 2 * H * FB_HD : nullptr;
+          float* kdst = (bias_mask & 2) ? bias_grad + H * FB_HD : nullptr;
+          stage_half(0, FB_COL_DV, 1.0f, valid, vdst, 0);
+          stage_half(1, FB_COL_DV + 32, 1.0f, valid, vdst, 1);
+          stage_half(2, FB_COL_DK, scale, valid, kdst, 0);
+          stage_half(3, FB_COL_DK + 32, scale, valid, kdst, 1);
+          fence_proxy_async();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(bar_free_vk);  // the MMA thread may overwrite dV / dK
+          if (quad_active) {
+            tma_store_3d_addr(&tm_dv, stage, h * FB_HD, row0, b);
+            tma_store_3d_addr(&tm_dv, stage + 2048, h * FB_HD + 32, row0, b);
+            tma_store_3d_addr(&tm_dk, stage + 4096, h * FB_HD, row0, b);
+            tma_store_3d_addr(&tm_dk, stage + 6144, h * FB_HD + 32, row0, b);
+            tma_store_commit();
+          }
+        }
+        if (kt == nkt - 1) {  // dQ of both query tiles (all of this item's MMAs have completed)
+          const bool q0 = quad * 32 < N, q1 = 128 + quad * 32 < N;
+          float* qdst = (bias_mask & 1) ? bias_grad : nullptr;
+          if (lane == 0) tma_store_wait_read<0>();  // the dV / dK stores above have finished reading the slots
+          __syncwarp();
+          if (q0) {
+            stage_half(0, FB_COL_DQ, scale, r < N, qdst, 0);
+            stage_half(1, FB_COL_DQ + 32, scale, r < N, qdst, 1);
+          }
+          if (q1) {
+            stage_half(2, FB_COL_DQ + 64, scale, 128 + r < N, qdst, 0);
+            stage_half(3, FB_COL_DQ + 96, scale, 128 + r < N, qdst, 1);
+          }
+          if (q0) fence_proxy_async();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive(bar_free_q);
+            if (q0) {
+              tma_store_3d_addr(&tm_dq, stage, h * FB_HD, quad * 32, b);
+              tma_store_3d_addr(&tm_dq, stage + 2048, h * FB_HD + 32, quad * 32, b);
             }
-            FB_CSTAMP(41);
-            tc_fence_before();
+            if (q1) {
+              tma_store_3d_addr(&tm_dq, stage + 4096, h * FB_HD, 128 + quad * 32, b);
+              tma_store_3d_addr(&tm_dq, stage + 6144, h * FB_HD + 32, 128 + quad * 32, b);
+            }
+            if (q0) tma_store_commit();
           }
         }
       }
     }
+    if (lane == 0) tma_store_wait_read<0>();  // the staging tiles must outlive the last TMA stores
   }
-  if (warp < 8 && lane == 0) tma_store_wait_read<0>();  // the staging tiles must outlive the last TMA stores
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
