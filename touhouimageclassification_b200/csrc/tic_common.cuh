@@ -279,6 +279,13 @@ TIC_DEVINL void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t (&r)[16]) {
       : "memory");
 }
 
+TIC_DEVINL void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               :
+               : "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+
 // ----------------------------------------------------------------------------------------------
 // CTA pairs (cta_group::2): two SMs of one cluster execute one 256-row UMMA; only the leader (cluster rank 0)
 // issues tcgen05.mma / tcgen05.commit, both CTAs load their own operand halves and own 128 accumulator rows.
