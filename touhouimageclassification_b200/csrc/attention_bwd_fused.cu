@@ -35,7 +35,8 @@ constexpr int FB_THREADS = 512;  // 8 compute warps + 1 TMA / MMA warp + 4 drain
 // drain warpgroups shrink to 88 -- 8 x 32 x (168 + 88) = the whole register file (the two sides must balance: asking for
 // more than the shrinking warps release blocks forever). Sixteen compute warps (16 query columns each, 88 registers)
 // measured slower, 0.312 vs 0.297 ms: the block period is set by the score -> P -> dV/dK -> next-score dependency
-// chain through the tensor pipe and the mbarrier hops, not by the elementwise pass.
+// chain through the tensor pipe and the mbarrier hops, not by the elementwise pass. Signalling the S^T and dP^T
+// halves of a block separately (four barriers per block instead of two) also measured slower (0.319 ms).
 constexpr int FB_REGS_COMPUTE = 168, FB_REGS_OTHER = 88;
 constexpr int FB_ROWS = 256;     // rows staged per operand
 constexpr int FB_HD = 64;
