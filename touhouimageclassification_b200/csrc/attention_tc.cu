@@ -471,7 +471,47 @@ int launch_bwd(const void* r1, const void* r2, long long ldr1, long long ldr2, c
   return check_launch(DKV ? "attention_bwd_dkv_tc" : "attention_bwd_dq_tc");
 }
 
+// ------------------------------------------------------------------------------------------------ delta
+// delta[b,h,n] = sum_d dO[b,n,h,d] * O[b,n,h,d]; one warp per token, two lanes per head.
+__global__ void __launch_bounds__(256)
+attn_delta_kernel(const __nv_bfloat16* __restrict__ o, long long ldo, const __nv_bfloat16* __restrict__ dout,
+                  long long lddo, float* __restrict__ delta, int B, int N, int H) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long tok = blockIdx.x * 8LL + warp;
+  if (tok >= static_cast<long long>(B) * N) return;
+  const int b = static_cast<int>(tok / N), n = static_cast<int>(tok - static_cast<long long>(b) * N);
+  for (int hbase = 0; hbase < H; hbase += 16) {  // warp-uniform trip count (full-mask shuffle below)
+    const int hh = hbase + (lane >> 1);
+    const bool valid = hh < H;
+    float s = 0.f;
+    if (valid) {
+      const uint4* po = reinterpret_cast<const uint4*>(o + tok * ldo + hh * AT_HD + (lane & 1) * 32);
+      const uint4* pd = reinterpret_cast<const uint4*>(dout + tok * lddo + hh * AT_HD + (lane & 1) * 32);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint4 a = __ldg(po + i), d = __ldg(pd + i);
+        s += bf16_lo(a.x) * bf16_lo(d.x) + bf16_hi(a.x) * bf16_hi(d.x);
+        s += bf16_lo(a.y) * bf16_lo(d.y) + bf16_hi(a.y) * bf16_hi(d.y);
+        s += bf16_lo(a.z) * bf16_lo(d.z) + bf16_hi(a.z) * bf16_hi(d.z);
+        s += bf16_lo(a.w) * bf16_lo(d.w) + bf16_hi(a.w) * bf16_hi(d.w);
+      }
+    }
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    if (valid && (lane & 1) == 0) delta[(static_cast<long long>(b) * H + hh) * N + n] = s;
+  }
+}
+
+
 }  // namespace
+
+int attention_delta(const void* o, long long ldo, const void* dout, long long lddo, float* delta, int B, int N, int H,
+                    cudaStream_t stream) {
+  const long long toks = static_cast<long long>(B) * N;
+  attn_delta_kernel<<<static_cast<int>((toks + 7) / 8), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(o), ldo,
+                                                                          reinterpret_cast<const __nv_bfloat16*>(dout),
+                                                                          lddo, delta, B, N, H);
+  return check_launch("attention_delta");
+}
 
 int attention_fwd_tc(const void* q, const void* k, const void* v, long long ld, void* o, long long ldo, float* lse,
                      int B, int N, int H, int head_dim, float scale, cudaStream_t stream) {

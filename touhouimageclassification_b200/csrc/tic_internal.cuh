@@ -67,13 +67,6 @@ int softmax_xent(const float* logits, const long long* hard, const float* soft, 
 int adamw_step(float* p, const float* g, float* m, float* v, void* shadow_bf16, long long n, float lr, float beta1,
                float beta2, float eps, float weight_decay, int step, float grad_scale, cudaStream_t stream);
 
-// attention.cu
-int attention_fwd(const void* q, const void* k, const void* v, long long ld, void* o, long long ldo, float* lse,
-                  int B, int N, int H, int head_dim, float scale, cudaStream_t stream);
-int attention_bwd(const void* q, const void* k, const void* v, long long ld, const void* o, long long ldo,
-                  const void* dout, long long lddo, const float* lse, float* delta, void* dq, void* dk, void* dv,
-                  long long lddqkv, int B, int N, int H, int head_dim, float scale, cudaStream_t stream);
-
 // augment.cu
 int augment_sample_params(long long seed, long long first_sample, int B, int H, int W, int size, int recipe,
                           int* ints_host, float* floats_host);
