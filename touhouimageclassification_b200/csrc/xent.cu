@@ -79,18 +79,19 @@ head_bwd_dw_kernel(const float* __restrict__ dlogits, const __nv_bfloat16* __res
   }
 }
 
-// One CTA. Row-wise log-softmax in fp32; loss = mean_b( -sum_c y[b,c] * logp[b,c] ) * (1/B);
+// One CTA of 32 warps (one row per warp at a time; a single CTA keeps the loss reduction order fixed, so the loss is
+// bit-reproducible). Row-wise log-softmax in fp32; loss = mean_b( -sum_c y[b,c] * logp[b,c] ) * (1/B);
 // dlogits[b,c] = (softmax[b,c] * sum_c y[b,c] - y[b,c]) * grad_scale   (grad_scale = upstream / global batch).
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 xent_kernel(const float* __restrict__ logits, const long long* __restrict__ hard, const float* __restrict__ soft,
             int B, int C, float grad_scale, int round_grad, float* __restrict__ loss, float* __restrict__ dlogits,
             int* __restrict__ correct) {
-  __shared__ float wloss[8];
-  __shared__ int wcorr[8];
+  __shared__ float wloss[32];
+  __shared__ int wcorr[32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float lsum = 0.f;
   int csum = 0;
-  for (int b = warp; b < B; b += 8) {
+  for (int b = warp; b < B; b += 32) {
     const float* lr = logits + static_cast<long long>(b) * C;
     float mx = -INFINITY;
     int amax = 0;
@@ -135,7 +136,7 @@ xent_kernel(const float* __restrict__ logits, const long long* __restrict__ hard
   if (threadIdx.x == 0) {
     float s = 0.f;
     int k = 0;
-    for (int w = 0; w < 8; ++w) { s += wloss[w]; k += wcorr[w]; }
+    for (int w = 0; w < 32; ++w) { s += wloss[w]; k += wcorr[w]; }
     *loss = s / static_cast<float>(B);
     if (correct) *correct = k;
   }
@@ -174,7 +175,7 @@ int softmax_xent(const float* logits, const long long* hard, const float* soft, 
     return set_error(kErrInvalidArg, "softmax_xent: exactly one of hard/soft targets must be given");
   if (B <= 0) return set_error(kErrInvalidArg, "softmax_xent: empty batch");
   ProfScope prof("softmax_xent", 0.0, static_cast<double>(B) * C * 8, stream);
-  xent_kernel<<<1, 256, 0, stream>>>(logits, hard, soft, B, C, grad_scale, round_grad, loss, dlogits, correct);
+  xent_kernel<<<1, 1024, 0, stream>>>(logits, hard, soft, B, C, grad_scale, round_grad, loss, dlogits, correct);
   return check_launch("softmax_xent");
 }
 
