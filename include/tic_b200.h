@@ -112,6 +112,18 @@ TIC_API int tic_attention_bwd_bias(const void* q, const void* k, const void* v, 
                                    void* dk, void* dv, int64_t lddqkv, float* qkv_bias_grad, int B, int N, int H,
                                    int head_dim, float scale, void* stream);
 
+/* Query-subset variants (N <= 224 forward, N <= 256 backward): only the first num_queries tokens of every image act as
+ * queries -- their rows of o / dout are read, their rows of o / dq written, lse is [B, H, num_queries] -- while all N
+ * tokens are keys. The engine uses num_queries = 1 in the LAST encoder layer: only the CLS row of that layer reaches
+ * the final LayerNorm and the classifier (modeling_vit.py:455,641-642), so every other row of its attention output,
+ * out-projection and MLP is dead work in the reference. qkv_bias_grad may be NULL. */
+TIC_API int tic_attention_fwd_nq(const void* q, const void* k, const void* v, int64_t ld, void* o, int64_t ldo, float* lse,
+                                 int B, int N, int num_queries, int H, int head_dim, float scale, void* stream);
+TIC_API int tic_attention_bwd_nq(const void* q, const void* k, const void* v, int64_t ld, const void* o, int64_t ldo,
+                                 const void* dout, int64_t lddo, const float* lse, float* delta_scratch, void* dq, void* dk,
+                                 void* dv, int64_t lddqkv, float* qkv_bias_grad, int B, int N, int num_queries, int H,
+                                 int head_dim, float scale, void* stream);
+
 /* ---- classifier head and fused softmax cross-entropy ----------------------------------------------
  * tic_head_fwd: logits[B,C] = h[B,D] W[C,D]^T + b (classifier, modeling_vit.py:641-642 [a11]).
  * tic_softmax_xent: F.cross_entropy forward + backward in one launch, integer targets (finetune.py:61

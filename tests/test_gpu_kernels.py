@@ -217,3 +217,25 @@ def test_patchify_is_exact_and_colsum():
     assert torch.equal(ops.patchify_f32(x), ref)       # pure data movement + one rounding: bit-exact
     dy = torch.randn(5000, 3072, device=dev).bfloat16()
     assert rel(ops.colsum_bf16(dy), dy.float().sum(0)) < 1e-5
+
+
+@pytest.mark.parametrize("B,N,H,Nq", [(3, 197, 4, 1), (2, 197, 2, 70), (2, 64, 2, 1), (2, 130, 2, 129), (4, 197, 16, 1)])
+def test_attention_query_subset(B, N, H, Nq):
+    """Only the first Nq tokens of every image are queries (Nq = 1: the CLS-only last layer): forward rows, logsumexp and
+    all three gradients equal the full computation with the other queries' upstream gradient set to zero."""
+    from touhouimageclassification_b200 import ops
+    D = H * 64
+    qkv = torch.randn(B * N, 3 * D, device=dev).bfloat16()
+    ctx_full, lse_full = ops.attention_fwd(qkv, B, N, H)
+    ctx, lse = ops.attention_fwd(qkv, B, N, H, num_queries=Nq)
+    cf, c = ctx_full.view(B, N, D), ctx.view(B, N, D)
+    assert torch.equal(c[:, :Nq], cf[:, :Nq]) and c[:, Nq:].abs().max() == 0
+    assert torch.equal(lse, lse_full[:, :, :Nq].contiguous())
+    dctx = torch.randn(B * N, D, device=dev).bfloat16()
+    dctx.view(B, N, D)[:, Nq:] = 0
+    ref = ops.attention_bwd(qkv, ctx_full, dctx, lse_full, B, N, H)
+    bg = torch.zeros(3 * D, device=dev)
+    got = ops.attention_bwd(qkv, ctx, dctx, lse, B, N, H, bias_grad=bg, num_queries=Nq)
+    assert torch.isfinite(got.float()).all()
+    assert rel(got, ref) < 2e-3 and got.view(B, N, 3 * D)[:, Nq:, :D].abs().max() == 0
+    assert (bg - got.float().sum(0)).abs().max() <= 1e-4 * max(1.0, got.float().sum(0).abs().max().item()) + 1e-5 * B * N

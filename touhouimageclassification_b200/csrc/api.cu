@@ -62,6 +62,18 @@ TIC_API int tic_attention_bwd_bias(const void* q, const void* k, const void* v, 
                           S(stream), qkv_bias_grad);
 }
 
+TIC_API int tic_attention_fwd_nq(const void* q, const void* k, const void* v, int64_t ld, void* o, int64_t ldo, float* lse,
+                                 int B, int N, int num_queries, int H, int head_dim, float scale, void* stream) {
+  return attention_fwd_tc(q, k, v, ld, o, ldo, lse, B, N, H, head_dim, scale, S(stream), num_queries);
+}
+TIC_API int tic_attention_bwd_nq(const void* q, const void* k, const void* v, int64_t ld, const void* o, int64_t ldo,
+                                 const void* dout, int64_t lddo, const float* lse, float* delta_scratch, void* dq, void* dk,
+                                 void* dv, int64_t lddqkv, float* qkv_bias_grad, int B, int N, int num_queries, int H,
+                                 int head_dim, float scale, void* stream) {
+  return attention_bwd_tc(q, k, v, ld, o, ldo, dout, lddo, lse, delta_scratch, dq, dk, dv, lddqkv, B, N, H, head_dim, scale,
+                          S(stream), qkv_bias_grad, 7, num_queries);
+}
+
 TIC_API int tic_head_fwd(const void* h_bf16, int64_t ldh, const void* w_bf16, const float* bias, int B, int D, int C,
                          int round_out_bf16, float* logits, void* stream) {
   return head_fwd(h_bf16, ldh, w_bf16, bias, B, D, C, round_out_bf16, logits, S(stream));

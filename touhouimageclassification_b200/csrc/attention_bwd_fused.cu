@@ -85,8 +85,9 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
                       const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
                       const __grid_constant__ CUtensorMap tm_o, const __grid_constant__ CUtensorMap tm_dq,
                       const __grid_constant__ CUtensorMap tm_dk, const __grid_constant__ CUtensorMap tm_dv,
-                      const float* __restrict__ lse, float* __restrict__ bias_grad, int bias_mask, int N, int H, int num_items, float scale,
-                      long long* __restrict__ trace) {
+                      const float* __restrict__ lse, float* __restrict__ bias_grad, int bias_mask, int N, int Nq, int H,
+                      int num_items, float scale, long long* __restrict__ trace) {
+  // N = keys per item; Nq = queries per item (the first Nq tokens of each image; Nq = 1 for the CLS-only last layer)
   // trace (dev tool, normally NULL): clock64 stamps of CTA 0 -- [0..63] compute warp 0, [64..127] the MMA thread
 #define FB_STAMP(slot) do { if (trace != nullptr && blockIdx.x == 0 && it == 3) trace[slot] = clock64(); } while (0)
   extern __shared__ uint8_t fb_smem_raw[];
@@ -115,8 +116,8 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkt = (N + 127) >> 7;             // key tiles of 128
-  const int nqb = (N + 63) >> 6;              // query blocks of 64
-  const int w_last = ((N - (nqb - 1) * 64) + 15) & ~15;  // width of the last query block (multiple of 16)
+  const int nqb = (Nq + 63) >> 6;             // query blocks of 64
+  const int w_last = ((Nq - (nqb - 1) * 64) + 15) & ~15;  // width of the last query block (multiple of 16)
   const int J = nkt * nqb;
 
   if (warp == 8) {
@@ -222,7 +223,10 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
             }
             const int kvalid = min(128, N - kt * 128);
             const int ks = (kvalid + 15) >> 4;
-            const uint64_t dS_mn = make_smem_desc_sw128(aS + qt * FB_STAGE_BYTES, 16384, 1024);
+            // staging tile of (key tile, query tile): with at most two query blocks there is one query tile and the two key
+            // tiles alternate between the two staging tiles (a tile is never rewritten while its dQ product may be reading it)
+            const int st = nqb <= 2 ? (kt & 1) : qt;
+            const uint64_t dS_mn = make_smem_desc_sw128(aS + st * FB_STAGE_BYTES, 16384, 1024);
             const uint64_t dK_mn = make_smem_desc_sw128(aK + kt * 16384, 8192, 1024);
             for (int k = 0; k < ks; ++k)
               umma_bf16_ss(tmem_base + FB_COL_DQ + qt * 64, dS_mn + 128 * k, dK_mn + 128 * k, idesc_dq, (kt > 0 || k > 0) ? 1u : 0u);
@@ -256,7 +260,7 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     const uint32_t ro = smem_u32(sO) + t * 128, rd = smem_u32(sDO) + t * 128;
     uint32_t ph_s = 0;  // bit b = parity of the next completion of bar_s[b]
     auto load_lse = [&](int item) -> float {  // per-query logsumexp, +inf past N: exp2(-inf) = 0
-      return (item < num_items && t < N) ? __ldg(lse + static_cast<long long>(item) * N + t) : INFINITY;
+      return (item < num_items && t < Nq) ? __ldg(lse + static_cast<long long>(item) * Nq + t) : INFINITY;
     };
     float L_next = load_lse(blockIdx.x);
     for (int it = 0, item = blockIdx.x; item < num_items; ++it, item += gridDim.x) {
@@ -314,7 +318,7 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
           tmem_st_32x32b_x16(lane_addr + FB_COL_DP + buf * 64 + half * 32, dw);
           // dS^T row -> staging tile of this query tile (chunk = 64-query block), zero for key rows past N so that the
           // dQ product never sees a non-finite value against the zero-filled K rows
-          const uint32_t dst = stage_row + (qb >> 1) * FB_STAGE_BYTES + (qb & 1) * 16384;
+          const uint32_t dst = stage_row + (nqb <= 2 ? (kt & 1) : (qb >> 1)) * FB_STAGE_BYTES + (qb & 1) * 16384;
 #pragma unroll
           for (int pc = 0; pc < 4; ++pc) {
             const uint32_t a = dst + (((half * 4 + pc) ^ sw) << 4);
@@ -400,17 +404,17 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
           }
         }
         if (kt == nkt - 1) {  // dQ of both query tiles (all of this item's MMAs have completed)
-          const bool q0 = quad * 32 < N, q1 = 128 + quad * 32 < N;
+          const bool q0 = quad * 32 < Nq, q1 = 128 + quad * 32 < Nq;
           float* qdst = (bias_mask & 1) ? bias_grad : nullptr;
           if (lane == 0) tma_store_wait_read<0>();  // the dV / dK stores above have finished reading the slots
           __syncwarp();
           if (q0) {
-            stage_half(0, FB_COL_DQ, scale, r < N, qdst, 0);
-            stage_half(1, FB_COL_DQ + 32, scale, r < N, qdst, 1);
+            stage_half(0, FB_COL_DQ, scale, r < Nq, qdst, 0);
+            stage_half(1, FB_COL_DQ + 32, scale, r < Nq, qdst, 1);
           }
           if (q1) {
-            stage_half(2, FB_COL_DQ + 64, scale, 128 + r < N, qdst, 0);
-            stage_half(3, FB_COL_DQ + 96, scale, 128 + r < N, qdst, 1);
+            stage_half(2, FB_COL_DQ + 64, scale, 128 + r < Nq, qdst, 0);
+            stage_half(3, FB_COL_DQ + 96, scale, 128 + r < Nq, qdst, 1);
           }
           if (q0) fence_proxy_async();
           tc_fence_before();
@@ -440,26 +444,29 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
 
 }  // namespace
 
-// q/k/v: [B*N, ...] pitch ld, head h at column h*64; o / dout: [B*N, H*64]; dq/dk/dv pitch ldg. bias_grad (optional):
+// q/k/v: [B*N, ...] pitch ld, head h at column h*64; o / dout: [B*N, H*64]; dq/dk/dv pitch ldg. Only the first Nq tokens
+// of every image are queries (their rows of o / dout are read, their rows of dq written; lse is [B, H, Nq]).
+// bias_grad (optional):
 // fp32 [3*H*64] laid out q | k | v, ACCUMULATES the column sums of dq (bias_mask bit 0) / dk (bit 1) / dv (bit 2).
 int attention_bwd_fused(const void* q, const void* k, const void* v, long long ld, const void* o, long long ldo,
                         const void* dout, long long lddo, const float* lse, void* dq, void* dk, void* dv, long long ldg,
-                        float* bias_grad, int bias_mask, int B, int N, int H, float scale, cudaStream_t stream) {
+                        float* bias_grad, int bias_mask, int B, int N, int Nq, int H, float scale, cudaStream_t stream) {
+  if (Nq <= 0 || Nq > N) return set_error(kErrInvalidArg, "attention_bwd_fused: Nq=%d must be in [1, N=%d]", Nq, N);
   if (N > FB_ROWS) return set_error(kErrUnsupported, "attention_bwd_fused: N=%d > %d", N, FB_ROWS);
   CUtensorMap tq, tk, tv, tdo, to, tdq, tdk, tdv;
   const uint64_t D = static_cast<uint64_t>(H) * FB_HD;
-  int rc = encode_tmap_3d_bf16(&tq, q, D, N, B, ld, static_cast<uint64_t>(N) * ld, 64, FB_ROWS);
+  int rc = encode_tmap_3d_bf16(&tq, q, D, Nq, B, ld, static_cast<uint64_t>(N) * ld, 64, FB_ROWS);
   if (rc) return rc;
   rc = encode_tmap_3d_bf16(&tk, k, D, N, B, ld, static_cast<uint64_t>(N) * ld, 64, FB_ROWS);
   if (rc) return rc;
   rc = encode_tmap_3d_bf16(&tv, v, D, N, B, ld, static_cast<uint64_t>(N) * ld, 64, FB_ROWS);
   if (rc) return rc;
-  rc = encode_tmap_3d_bf16(&tdo, dout, D, N, B, lddo, static_cast<uint64_t>(N) * lddo, 64, FB_ROWS);
+  rc = encode_tmap_3d_bf16(&tdo, dout, D, Nq, B, lddo, static_cast<uint64_t>(N) * lddo, 64, FB_ROWS);
   if (rc) return rc;
-  rc = encode_tmap_3d_bf16(&to, o, D, N, B, ldo, static_cast<uint64_t>(N) * ldo, 64, FB_ROWS);
+  rc = encode_tmap_3d_bf16(&to, o, D, Nq, B, ldo, static_cast<uint64_t>(N) * ldo, 64, FB_ROWS);
   if (rc) return rc;
   // outputs: 32-column x 32-row boxes (one compute warp's tile), 64-byte swizzle
-  rc = encode_tmap_3d_bf16_sw(&tdq, dq, D, N, B, ldg, static_cast<uint64_t>(N) * ldg, 32, 32, 64);
+  rc = encode_tmap_3d_bf16_sw(&tdq, dq, D, Nq, B, ldg, static_cast<uint64_t>(N) * ldg, 32, 32, 64);
   if (rc) return rc;
   rc = encode_tmap_3d_bf16_sw(&tdk, dk, D, N, B, ldg, static_cast<uint64_t>(N) * ldg, 32, 32, 64);
   if (rc) return rc;
@@ -488,7 +495,7 @@ int attention_bwd_fused(const void* q, const void* k, const void* v, long long l
     for (int i = 0; i < 128; ++i) trace[i] = 0;
   }
   attn_bwd_fused_kernel<<<grid, FB_THREADS, FB_SMEM, stream>>>(
-      tq, tk, tv, tdo, to, tdq, tdk, tdv, lse, bias_grad, bias_mask, N, H, items, scale, trace);
+      tq, tk, tv, tdo, to, tdq, tdk, tdv, lse, bias_grad, bias_mask, N, Nq, H, items, scale, trace);
   if (trace != nullptr) {
     cudaDeviceSynchronize();
     const long long t0 = trace[0];

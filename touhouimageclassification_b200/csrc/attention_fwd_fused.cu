@@ -47,7 +47,10 @@ TIC_DEVINL void ff_st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t 
 __global__ void __launch_bounds__(FF_THREADS, 1)
 attn_fwd_fused_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                       const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_o,
-                      float* __restrict__ lse, int N, int H, int num_items, float scale, long long* __restrict__ trace) {
+                      float* __restrict__ lse, int N, int Nq, int H, int num_items, float scale,
+                      long long* __restrict__ trace) {
+  // N = keys per item; Nq = queries per item (the first Nq tokens of each image: Nq = N normally, Nq = 1 when only the
+  // CLS row of the last encoder layer is needed)
   // trace (dev tool, normally NULL): clock64 stamps of CTA 0, third item -- [0..31] warp 0, [32..63] warp 4, [64..] MMA thread
 #define FF_STAMP(slot) do { if (trace != nullptr && blockIdx.x == 0 && it == 2) trace[slot] = clock64(); } while (0)
   extern __shared__ uint8_t ff_smem_raw[];
@@ -62,7 +65,7 @@ attn_fwd_fused_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nqt = (N + 127) >> 7;          // query tiles in use (1 or 2)
+  const int nqt = (Nq + 127) >> 7;         // query tiles in use (1 or 2)
   const int nk = (N + 15) & ~15;           // keys rounded up to the UMMA N / K granularity (padded keys are zero rows)
 
   if (warp == 8) {
@@ -137,7 +140,7 @@ attn_fwd_fused_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     const uint32_t lane_addr = tmem_base + t * 256 + (static_cast<uint32_t>(quad * 32) << 16);
     const float c2 = scale * FF_LOG2E;
     const int row = t * 128 + quad * 32 + lane;      // query row within the item
-    const bool warp_active = t * 128 + quad * 32 < N;  // warps whose 32 rows are all padding only keep the barriers moving
+    const bool warp_active = t * 128 + quad * 32 < Nq;  // warps whose 32 rows are all padding only keep the barriers moving
     const uint32_t out_tile = smem_u32(sOut) + warp * 4096;
     const int nchunk = (N + 31) >> 5;                // 32-column chunks that hold at least one valid key
     const int tail = N - (nchunk - 1) * 32;          // valid keys in the last chunk (1..32)
@@ -266,7 +269,7 @@ attn_fwd_fused_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
             tma_store_3d_addr(&tm_o, out_tile, h * FF_HD, t * 128 + quad * 32, b);
             tma_store_commit();
           }
-          if (lse != nullptr && row < N) lse[static_cast<long long>(item) * N + row] = (mx + log2f(l)) * FF_LN2;
+          if (lse != nullptr && row < Nq) lse[static_cast<long long>(item) * Nq + row] = (mx + log2f(l)) * FF_LN2;
         }
         FF_WSTAMP(6);
       }
@@ -281,19 +284,21 @@ attn_fwd_fused_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
 
 }  // namespace
 
-// q/k/v: [B*N, ...] with row pitch ld, head h at column h*64; o: [B*N, H*64] pitch ldo; lse: [B, H, N] or NULL.
+// q/k/v: [B*N, ...] with row pitch ld, head h at column h*64; o: [B*N, H*64] pitch ldo; lse: [B, H, Nq] or NULL.
+// Only the first Nq tokens of every image act as queries (their rows of o / lse are written); all N are keys.
 int attention_fwd_fused(const void* q, const void* k, const void* v, long long ld, void* o, long long ldo, float* lse, int B,
-                        int N, int H, float scale, cudaStream_t stream) {
+                        int N, int Nq, int H, float scale, cudaStream_t stream) {
   if (N > FF_KV) return set_error(kErrUnsupported, "attention_fwd_fused: N=%d > %d", N, FF_KV);
+  if (Nq <= 0 || Nq > N) return set_error(kErrInvalidArg, "attention_fwd_fused: Nq=%d must be in [1, N=%d]", Nq, N);
   CUtensorMap tq, tk, tv, to;
   const uint64_t D = static_cast<uint64_t>(H) * FF_HD;
-  int rc = encode_tmap_3d_bf16(&tq, q, D, N, B, ld, static_cast<uint64_t>(N) * ld, 64, 256);
+  int rc = encode_tmap_3d_bf16(&tq, q, D, Nq, B, ld, static_cast<uint64_t>(N) * ld, 64, 256);
   if (rc) return rc;
   rc = encode_tmap_3d_bf16(&tk, k, D, N, B, ld, static_cast<uint64_t>(N) * ld, 64, FF_KV);
   if (rc) return rc;
   rc = encode_tmap_3d_bf16(&tv, v, D, N, B, ld, static_cast<uint64_t>(N) * ld, 64, FF_KV);
   if (rc) return rc;
-  rc = encode_tmap_3d_bf16(&to, o, D, N, B, ldo, static_cast<uint64_t>(N) * ldo, 64, 32);  // one warp's 32-row tile
+  rc = encode_tmap_3d_bf16(&to, o, D, Nq, B, ldo, static_cast<uint64_t>(N) * ldo, 64, 32);  // one warp's 32-row tile
   if (rc) return rc;
   static bool attr_set = false;
   if (!attr_set) {
@@ -316,7 +321,7 @@ int attention_fwd_fused(const void* q, const void* k, const void* v, long long l
     cudaMallocManaged(&trace, 128 * sizeof(long long));
     for (int i = 0; i < 128; ++i) trace[i] = 0;
   }
-  attn_fwd_fused_kernel<<<grid, FF_THREADS, FF_SMEM, stream>>>(tq, tk, tv, to, lse, N, H, items, scale, trace);
+  attn_fwd_fused_kernel<<<grid, FF_THREADS, FF_SMEM, stream>>>(tq, tk, tv, to, lse, N, Nq, H, items, scale, trace);
   if (trace != nullptr) {
     cudaDeviceSynchronize();
     const long long t0 = trace[0];

@@ -514,7 +514,9 @@ int attention_delta(const void* o, long long ldo, const void* dout, long long ld
 }
 
 int attention_fwd_tc(const void* q, const void* k, const void* v, long long ld, void* o, long long ldo, float* lse,
-                     int B, int N, int H, int head_dim, float scale, cudaStream_t stream) {
+                     int B, int N, int H, int head_dim, float scale, cudaStream_t stream, int Nq) {
+  if (Nq <= 0) Nq = N;
+  if (Nq != N && N > 224) return set_error(kErrUnsupported, "attention: a query subset needs N <= 224 (N=%d)", N);
   if (head_dim != AT_HD) return set_error(kErrUnsupported, "attention: head_dim=%d (only 64 is supported)", head_dim);
   if (B <= 0 || N <= 0) return kOk;
   if ((ld % 8) || (reinterpret_cast<uintptr_t>(q) & 15) || (reinterpret_cast<uintptr_t>(k) & 15) ||
@@ -524,7 +526,7 @@ int attention_fwd_tc(const void* q, const void* k, const void* v, long long ld, 
   if (N <= 224) {
     if ((ldo % 8) || (reinterpret_cast<uintptr_t>(o) & 15))
       return set_error(kErrInvalidArg, "attention: o must be 16-byte aligned with a pitch that is a multiple of 8");
-    return attention_fwd_fused(q, k, v, ld, o, ldo, lse, B, N, H, scale, stream);  // persistent, one key block
+    return attention_fwd_fused(q, k, v, ld, o, ldo, lse, B, N, Nq, H, scale, stream);  // persistent, one key block
   }
   return launch_fwd<128>(q, k, v, ld, o, ldo, lse, B, N, H, scale, stream);
 }
@@ -532,14 +534,16 @@ int attention_fwd_tc(const void* q, const void* k, const void* v, long long ld, 
 int attention_bwd_tc(const void* q, const void* k, const void* v, long long ld, const void* o, long long ldo,
                      const void* dout, long long lddo, const float* lse, float* delta, void* dq, void* dk, void* dv,
                      long long lddqkv, int B, int N, int H, int head_dim, float scale, cudaStream_t stream,
-                     float* bias_grad, int bias_mask) {
+                     float* bias_grad, int bias_mask, int Nq) {
+  if (Nq <= 0) Nq = N;
+  if (Nq != N && N > 256) return set_error(kErrUnsupported, "attention_bwd: a query subset needs N <= 256 (N=%d)", N);
   if (head_dim != AT_HD) return set_error(kErrUnsupported, "attention: head_dim=%d (only 64 is supported)", head_dim);
   if (B <= 0 || N <= 0) return kOk;
   if ((ld % 8) || (lddo % 8) || (lddqkv % 8) || (ldo % 8))
     return set_error(kErrInvalidArg, "attention_bwd: pitches must be multiples of 8");
   if (N <= 256) {  // whole head in shared memory: one fused kernel (delta, dQ, dK, dV, QKV bias gradient)
     ProfScope prof("attention_bwd", 10.0 * B * H * static_cast<double>(N) * N * AT_HD, 16.0 * B * H * static_cast<double>(N) * AT_HD, stream);
-    return attention_bwd_fused(q, k, v, ld, o, ldo, dout, lddo, lse, dq, dk, dv, lddqkv, bias_grad, bias_mask, B, N, H, scale, stream);
+    return attention_bwd_fused(q, k, v, ld, o, ldo, dout, lddo, lse, dq, dk, dv, lddqkv, bias_grad, bias_mask, B, N, Nq, H, scale, stream);
   }
   ProfScope prof("attention_bwd", 10.0 * B * H * static_cast<double>(N) * N * AT_HD, 16.0 * B * H * static_cast<double>(N) * AT_HD, stream);
   int rc = attention_delta(o, ldo, dout, lddo, delta, B, N, H, stream);

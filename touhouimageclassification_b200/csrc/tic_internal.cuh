@@ -75,8 +75,9 @@ int augment_patchify(const void* images_u8, int B, int H, int W, const int* ints
                      cudaStream_t stream);
 
 // attention_tc.cu (tcgen05 / TMEM / TMA)
+// Nq (0 = N): only the first Nq tokens of every image act as queries (N <= 224 / 256 paths only); lse is [B, H, Nq].
 int attention_fwd_tc(const void* q, const void* k, const void* v, long long ld, void* o, long long ldo, float* lse,
-                     int B, int N, int H, int head_dim, float scale, cudaStream_t stream);
+                     int B, int N, int H, int head_dim, float scale, cudaStream_t stream, int Nq = 0);
 
 // bias_grad (optional, fp32 [3 * H * 64] = q | k | v) ACCUMULATES the column sums of dq / dk / dv (QKV bias gradient).
 // N <= 256 runs the single fused kernel of attention_bwd_fused.cu (delta is not used); longer sequences run the
@@ -84,14 +85,14 @@ int attention_fwd_tc(const void* q, const void* k, const void* v, long long ld, 
 int attention_bwd_tc(const void* q, const void* k, const void* v, long long ld, const void* o, long long ldo,
                      const void* dout, long long lddo, const float* lse, float* delta, void* dq, void* dk, void* dv,
                      long long lddqkv, int B, int N, int H, int head_dim, float scale, cudaStream_t stream,
-                     float* bias_grad = nullptr, int bias_mask = 7);
+                     float* bias_grad = nullptr, int bias_mask = 7, int Nq = 0);
 // attention_fwd_fused.cu (N <= 224: persistent kernel, both query tiles of a head per CTA, operands prefetched)
 int attention_fwd_fused(const void* q, const void* k, const void* v, long long ld, void* o, long long ldo, float* lse, int B,
-                        int N, int H, float scale, cudaStream_t stream);
+                        int N, int Nq, int H, float scale, cudaStream_t stream);
 // attention_bwd_fused.cu
 int attention_bwd_fused(const void* q, const void* k, const void* v, long long ld, const void* o, long long ldo,
                         const void* dout, long long lddo, const float* lse, void* dq, void* dk, void* dv, long long ldg,
-                        float* bias_grad, int bias_mask, int B, int N, int H, float scale, cudaStream_t stream);
+                        float* bias_grad, int bias_mask, int B, int N, int Nq, int H, float scale, cudaStream_t stream);
 int attention_delta(const void* o, long long ldo, const void* dout, long long lddo, float* delta, int B, int N, int H,
                     cudaStream_t stream);
 

@@ -88,25 +88,42 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, dres=None):
     return dx, dxb, dgamma, dbeta, dxsum
 
 
-def attention_fwd(qkv, B, N, H, scale=0.125, need_lse=True):
-    """qkv: bf16 [B*N, 3*H*64] (q | k | v column blocks). Returns ctx bf16 [B*N, H*64], lse fp32 [B,H,N]."""
+def attention_fwd(qkv, B, N, H, scale=0.125, need_lse=True, num_queries=None):
+    """qkv: bf16 [B*N, 3*H*64] (q | k | v column blocks). Returns ctx bf16 [B*N, H*64], lse fp32 [B,H,N].
+    ``num_queries`` = Nq: only the first Nq tokens of every image are queries (other ctx rows are left zero, lse [B,H,Nq])."""
     _require_cuda(qkv)
     D = H * 64
     assert qkv.shape == (B * N, 3 * D) and qkv.dtype == torch.bfloat16 and qkv.is_contiguous()
-    ctx = torch.empty((B * N, D), device=qkv.device, dtype=torch.bfloat16)
-    lse = torch.empty((B, H, N), device=qkv.device, dtype=torch.float32) if need_lse else None
+    Nq = N if num_queries is None else num_queries
+    ctx = (torch.empty if Nq == N else torch.zeros)((B * N, D), device=qkv.device, dtype=torch.bfloat16)
+    lse = torch.empty((B, H, Nq), device=qkv.device, dtype=torch.float32) if need_lse else None
     base = qkv.data_ptr()
-    _lib.check(_lib.load().tic_attention_fwd(c_void_p(base), c_void_p(base + 2 * D), c_void_p(base + 4 * D), c_i64(3 * D),
-                                             _p(ctx), c_i64(D), _p(lse), c_int(B), c_int(N), c_int(H), c_int(64),
-                                             c_float(scale), _s()))
+    if num_queries is None:
+        _lib.check(_lib.load().tic_attention_fwd(c_void_p(base), c_void_p(base + 2 * D), c_void_p(base + 4 * D), c_i64(3 * D),
+                                                 _p(ctx), c_i64(D), _p(lse), c_int(B), c_int(N), c_int(H), c_int(64),
+                                                 c_float(scale), _s()))
+    else:
+        _lib.check(_lib.load().tic_attention_fwd_nq(c_void_p(base), c_void_p(base + 2 * D), c_void_p(base + 4 * D),
+                                                    c_i64(3 * D), _p(ctx), c_i64(D), _p(lse), c_int(B), c_int(N), c_int(Nq),
+                                                    c_int(H), c_int(64), c_float(scale), _s()))
     return ctx, lse
 
 
-def attention_bwd(qkv, ctx, dctx, lse, B, N, H, scale=0.125, bias_grad=None):
-    """dqkv [B*N, 3D] bf16. ``bias_grad`` (fp32 [3D], optional) accumulates the column sums of dqkv (QKV bias gradient)."""
+def attention_bwd(qkv, ctx, dctx, lse, B, N, H, scale=0.125, bias_grad=None, num_queries=None):
+    """dqkv [B*N, 3D] bf16. ``bias_grad`` (fp32 [3D], optional) accumulates the column sums of dqkv (QKV bias gradient).
+    ``num_queries`` = Nq: only the first Nq tokens of every image are queries (dq of the other rows is left zero)."""
     _require_cuda(qkv, ctx, dctx, lse)
     D = H * 64
-    dqkv = torch.empty_like(qkv)
+    dqkv = torch.empty_like(qkv) if num_queries is None else torch.zeros_like(qkv)
+    if num_queries is not None:
+        delta = torch.empty((B, H, N), device=qkv.device, dtype=torch.float32)
+        base, dbase = qkv.data_ptr(), dqkv.data_ptr()
+        _lib.check(_lib.load().tic_attention_bwd_nq(c_void_p(base), c_void_p(base + 2 * D), c_void_p(base + 4 * D),
+                                                    c_i64(3 * D), _p(ctx), c_i64(D), _p(dctx), c_i64(D), _p(lse), _p(delta),
+                                                    c_void_p(dbase), c_void_p(dbase + 2 * D), c_void_p(dbase + 4 * D),
+                                                    c_i64(3 * D), _p(bias_grad), c_int(B), c_int(N), c_int(num_queries),
+                                                    c_int(H), c_int(64), c_float(scale), _s()))
+        return dqkv
     delta = torch.empty((B, H, N), device=qkv.device, dtype=torch.float32)
     base, dbase = qkv.data_ptr(), dqkv.data_ptr()
     if bias_grad is None:
