@@ -13,6 +13,8 @@
 #include "tic_b200.h"
 #include "tic_internal.cuh"
 
+#include <cstdlib>
+
 namespace tic {
 
 namespace {
@@ -138,6 +140,14 @@ int pick_splits(int Mo, int No, int K) {
   return best;
 }
 
+// The last encoder layer is evaluated on the CLS rows only when the sequence fits the fused attention kernels
+// (they take a query subset; the long-sequence kernels do not).
+bool cls_only_last_layer(const tic_vit_config* c) {
+  static const bool full = std::getenv("TIC_FULL_LAST_LAYER") != nullptr;  // development knob: A/B against the full layer
+  const int G = c->image_size / 16;
+  return !full && G * G + 1 <= 224;
+}
+
 #define TIC_TRY(expr)        \
   do {                       \
     int rc__ = (expr);       \
@@ -205,17 +215,34 @@ int vit_forward(const tic_vit_config* c, const float* P32, const void* P16v, con
     float *mean1 = training ? stats : nullptr, *rstd1 = training ? stats + ss : nullptr;
     float *mean2 = training ? stats + 2 * ss : nullptr, *rstd2 = training ? stats + 3 * ss : nullptr;
 
+    // The classifier reads only the CLS row of the last layer's output (modeling_vit.py:641), and inside a layer a
+    // token's output depends on the other tokens only through the keys and values. So the last layer projects K and V
+    // for every token but runs the query projection, the attention rows, the output projection and the MLP on the
+    // B CLS rows alone (row pitch N*width in the same buffers). Needs the fused attention kernels (query subsets).
+    const bool cls_only = cls_only_last_layer(c) && l == c->layers - 1;
+    const int rows = cls_only ? B : M;
+    const long long rm = cls_only ? N : 1;  // row pitch multiplier of the per-token buffers
+
     TIC_TRY(layernorm_fwd(x_in, D, p32 + L.ln1_w, p32 + L.ln1_b, c->ln_eps, M, D, h1, D, nullptr, 0, mean1, rstd1, st));
-    TIC_TRY(gemm_bf16(h1, D, false, p16 + L.qkv_w, D, false, M, 3 * D, D, kEpiBf16, qkv, 3 * D, nullptr, 0,
-                      p32 + L.qkv_b, nullptr, 0, 0, 1, st));
-    TIC_TRY(attention_fwd_tc(qkv, qkv + D, qkv + 2 * D, 3 * D, ctx, D, training ? lse : nullptr, B, N, H, 64, scale, st));
-    TIC_TRY(gemm_bf16(ctx, D, false, p16 + L.o_w, D, false, M, D, D, kEpiF32Resid, xmid, D, nullptr, 0, p32 + L.o_b,
-                      x_in, D, 0, 1, st));
-    TIC_TRY(layernorm_fwd(xmid, D, p32 + L.ln2_w, p32 + L.ln2_b, c->ln_eps, M, D, h2, D, nullptr, 0, mean2, rstd2, st));
-    TIC_TRY(gemm_bf16(h2, D, false, p16 + L.fc1_w, D, false, M, F, D, kEpiBf16Gelu, act, F, pre, F, p32 + L.fc1_b,
-                      nullptr, 0, 0, 1, st));
-    TIC_TRY(gemm_bf16(act, F, false, p16 + L.fc2_w, F, false, M, D, F, kEpiF32Resid, x_out, D, nullptr, 0,
-                      p32 + L.fc2_b, xmid, D, 0, 1, st));
+    if (!cls_only) {
+      TIC_TRY(gemm_bf16(h1, D, false, p16 + L.qkv_w, D, false, M, 3 * D, D, kEpiBf16, qkv, 3 * D, nullptr, 0,
+                        p32 + L.qkv_b, nullptr, 0, 0, 1, st));
+    } else {
+      TIC_TRY(gemm_bf16(h1, D, false, p16 + L.qkv_w + static_cast<long long>(D) * D, D, false, M, 2 * D, D, kEpiBf16,
+                        qkv + D, 3 * D, nullptr, 0, p32 + L.qkv_b + D, nullptr, 0, 0, 1, st));
+      TIC_TRY(gemm_bf16(h1, rm * D, false, p16 + L.qkv_w, D, false, B, D, D, kEpiBf16, qkv, rm * 3 * D, nullptr, 0,
+                        p32 + L.qkv_b, nullptr, 0, 0, 1, st));
+    }
+    TIC_TRY(attention_fwd_tc(qkv, qkv + D, qkv + 2 * D, 3 * D, ctx, D, training ? lse : nullptr, B, N, H, 64, scale, st,
+                             cls_only ? 1 : 0));
+    TIC_TRY(gemm_bf16(ctx, rm * D, false, p16 + L.o_w, D, false, rows, D, D, kEpiF32Resid, xmid, rm * D, nullptr, 0,
+                      p32 + L.o_b, x_in, rm * D, 0, 1, st));
+    TIC_TRY(layernorm_fwd(xmid, rm * D, p32 + L.ln2_w, p32 + L.ln2_b, c->ln_eps, rows, D, h2, rm * D, nullptr, 0, mean2,
+                          rstd2, st));
+    TIC_TRY(gemm_bf16(h2, rm * D, false, p16 + L.fc1_w, D, false, rows, F, D, kEpiBf16Gelu, act, rm * F, pre, rm * F,
+                      p32 + L.fc1_b, nullptr, 0, 0, 1, st));
+    TIC_TRY(gemm_bf16(act, rm * F, false, p16 + L.fc2_w, F, false, rows, D, F, kEpiF32Resid, x_out, rm * D, nullptr, 0,
+                      p32 + L.fc2_b, xmid, rm * D, 0, 1, st));
   }
 
   // ---- final LayerNorm on the CLS rows only (the only rows the classifier reads) + head
@@ -258,8 +285,9 @@ int vit_backward(const tic_vit_config* c, const float* P32, const void* P16v, in
       TIC_TRY(head_bwd(dlogits, ws + w.hcls, D, P16 + L.cls_w, B, D, C, need_dh ? ws + w.dhcls : nullptr, D,
                        G + L.cls_w, G + L.cls_b, st));
       if (head_only) continue;
+      // only the CLS rows carry gradient here; the bf16 copy is read at CLS rows alone when the last layer is CLS-only
       cudaError_t e1 = cudaMemsetAsync(dx, 0, static_cast<size_t>(M) * D * 4, st);
-      cudaError_t e2 = cudaMemsetAsync(dxb, 0, static_cast<size_t>(M) * D * 2, st);
+      cudaError_t e2 = cls_only_last_layer(c) ? cudaSuccess : cudaMemsetAsync(dxb, 0, static_cast<size_t>(M) * D * 2, st);
       if (e1 != cudaSuccess || e2 != cudaSuccess) return set_error(kErrCuda, "vit_backward: memset failed");
       const float* x_last = reinterpret_cast<const float*>(ws + w.x + w.s_x * Lyr);
       const float* fstats = reinterpret_cast<const float*>(ws + w.stats + w.s_stats * 4 * Lyr);
@@ -288,37 +316,55 @@ int vit_backward(const tic_vit_config* c, const float* P32, const void* P16v, in
       const long long ss = w.s_stats / 4;
       const float *mean1 = stats, *rstd1 = stats + ss, *mean2 = stats + 2 * ss, *rstd2 = stats + 3 * ss;
 
+      const bool cls_only = cls_only_last_layer(c) && l == Lyr - 1;  // see vit_forward: this layer ran on the CLS rows
+      const int rows = cls_only ? B : M;
+      const long long rm = cls_only ? N : 1;
+
       // fc2: x_out = xmid + act W2^T + b2        (dy = dxb, the bf16 copy of the residual-stream gradient)
-      TIC_TRY(gemm_bf16(dxb, D, false, p16 + L.fc2_w, F, true, M, F, D, kEpiBf16DGelu, dact, F, nullptr, 0, nullptr, pre,
-                        F, 0, 1, st, g + L.fc1_b));  // dact <- dpre = (dy W2) * gelu'(pre) (saved by the forward); fc1 bias grad = colsum(dpre)
-      TIC_TRY(gemm_bf16(dxb, D, true, act, F, true, D, F, M, kEpiF32Atomic, g + L.fc2_w, F, nullptr, 0, nullptr, nullptr,
-                        0, 0, pick_splits(D, F, M), st));
+      TIC_TRY(gemm_bf16(dxb, rm * D, false, p16 + L.fc2_w, F, true, rows, F, D, kEpiBf16DGelu, dact, rm * F, nullptr, 0,
+                        nullptr, pre, rm * F, 0, 1, st, g + L.fc1_b));  // dact <- dpre = (dy W2) * gelu'(pre) (saved by the forward); fc1 bias grad = colsum(dpre)
+      TIC_TRY(gemm_bf16(dxb, rm * D, true, act, rm * F, true, D, F, rows, kEpiF32Atomic, g + L.fc2_w, F, nullptr, 0,
+                        nullptr, nullptr, 0, 0, pick_splits(D, F, rows), st));
       // fc1: pre = h2 W1^T + b1
-      TIC_TRY(gemm_bf16(dact, F, false, p16 + L.fc1_w, D, true, M, D, F, kEpiBf16, dh, D, nullptr, 0, nullptr, nullptr, 0,
-                        0, 1, st));
-      TIC_TRY(gemm_bf16(dact, F, true, h2, D, true, F, D, M, kEpiF32Atomic, g + L.fc1_w, D, nullptr, 0, nullptr, nullptr,
-                        0, 0, pick_splits(F, D, M), st));
+      TIC_TRY(gemm_bf16(dact, rm * F, false, p16 + L.fc1_w, D, true, rows, D, F, kEpiBf16, dh, rm * D, nullptr, 0, nullptr,
+                        nullptr, 0, 0, 1, st));
+      TIC_TRY(gemm_bf16(dact, rm * F, true, h2, rm * D, true, F, D, rows, kEpiF32Atomic, g + L.fc1_w, D, nullptr, 0,
+                        nullptr, nullptr, 0, 0, pick_splits(F, D, rows), st));
       // layernorm_after + residual
-      TIC_TRY(layernorm_bwd(dh, D, xmid, D, mean2, rstd2, p32 + L.ln2_w, dx, D, M, D, dx, D, dxb, D, g + L.ln2_w,
-                            g + L.ln2_b, g + L.o_b, st));  // + out-proj bias grad = colsum(dxb)
+      TIC_TRY(layernorm_bwd(dh, rm * D, xmid, rm * D, mean2, rstd2, p32 + L.ln2_w, dx, rm * D, rows, D, dx, rm * D, dxb,
+                            rm * D, g + L.ln2_w, g + L.ln2_b, g + L.o_b, st));  // + out-proj bias grad = colsum(dxb)
       // attention output projection: xmid = x_in + ctx Wo^T + bo
       // dctx = dxb Wo; its column sums are the VALUE bias gradient: sum_k dV[k,:] = sum_q (sum_k P[q,k]) dO[q,:] = sum_q dO[q,:]
       // because every softmax row sums to one -- accumulated for free in this GEMM's epilogue.
-      TIC_TRY(gemm_bf16(dxb, D, false, p16 + L.o_w, D, true, M, D, D, kEpiBf16, dctx, D, nullptr, 0, nullptr, nullptr, 0,
-                        0, 1, st, g + L.qkv_b + 2 * D));
-      TIC_TRY(gemm_bf16(dxb, D, true, ctx, D, true, D, D, M, kEpiF32Atomic, g + L.o_w, D, nullptr, 0, nullptr, nullptr, 0,
-                        0, pick_splits(D, D, M), st));
+      TIC_TRY(gemm_bf16(dxb, rm * D, false, p16 + L.o_w, D, true, rows, D, D, kEpiBf16, dctx, rm * D, nullptr, 0, nullptr,
+                        nullptr, 0, 0, 1, st, g + L.qkv_b + 2 * D));
+      TIC_TRY(gemm_bf16(dxb, rm * D, true, ctx, rm * D, true, D, D, rows, kEpiF32Atomic, g + L.o_w, D, nullptr, 0, nullptr,
+                        nullptr, 0, 0, pick_splits(D, D, rows), st));
       // attention core
       TIC_TRY(attention_bwd_tc(qkv, qkv + D, qkv + 2 * D, 3 * D, ctx, D, dctx, D, lse, delta, dqkv, dqkv + D, dqkv + 2 * D,
-                            3 * D, B, N, H, 64, scale, st, g + L.qkv_b, 1));
+                            3 * D, B, N, H, 64, scale, st, g + L.qkv_b, 1, cls_only ? 1 : 0));
       // bias gradients of the fused QKV Linear: query = colsum(dq), accumulated by the attention backward (mask 1);
       // value = colsum(dctx), above; key = exactly 0 (sum_k dS[q,k] = 0: softmax is invariant to a shift of all keys,
       // SURVEY Appendix D.3 -- the reference computes ~1e-10 of rounding noise here), so it is left untouched.
       // fused QKV projection
-      TIC_TRY(gemm_bf16(dqkv, 3 * D, false, p16 + L.qkv_w, D, true, M, D, 3 * D, kEpiBf16, dh, D, nullptr, 0, nullptr,
-                        nullptr, 0, 0, 1, st));
-      TIC_TRY(gemm_bf16(dqkv, 3 * D, true, h1, D, true, 3 * D, D, M, kEpiF32Atomic, g + L.qkv_w, D, nullptr, 0, nullptr,
-                        nullptr, 0, 0, pick_splits(3 * D, D, M), st));
+      if (!cls_only) {
+        TIC_TRY(gemm_bf16(dqkv, 3 * D, false, p16 + L.qkv_w, D, true, M, D, 3 * D, kEpiBf16, dh, D, nullptr, 0, nullptr,
+                          nullptr, 0, 0, 1, st));
+        TIC_TRY(gemm_bf16(dqkv, 3 * D, true, h1, D, true, 3 * D, D, M, kEpiF32Atomic, g + L.qkv_w, D, nullptr, 0, nullptr,
+                          nullptr, 0, 0, pick_splits(3 * D, D, M), st));
+      } else {
+        // dq exists on the CLS rows only: every row gets its key/value part (K = 2D), then the CLS rows are recomputed
+        // with all three parts (K = 3D); the weight gradient is taken per part over the rows that have it.
+        const long long kv = static_cast<long long>(D) * D;
+        TIC_TRY(gemm_bf16(dqkv + D, 3 * D, false, p16 + L.qkv_w + kv, D, true, M, D, 2 * D, kEpiBf16, dh, D, nullptr, 0,
+                          nullptr, nullptr, 0, 0, 1, st));
+        TIC_TRY(gemm_bf16(dqkv, rm * 3 * D, false, p16 + L.qkv_w, D, true, B, D, 3 * D, kEpiBf16, dh, rm * D, nullptr, 0,
+                          nullptr, nullptr, 0, 0, 1, st));
+        TIC_TRY(gemm_bf16(dqkv + D, 3 * D, true, h1, D, true, 2 * D, D, M, kEpiF32Atomic, g + L.qkv_w + kv, D, nullptr, 0,
+                          nullptr, nullptr, 0, 0, pick_splits(2 * D, D, M), st));
+        TIC_TRY(gemm_bf16(dqkv, rm * 3 * D, true, h1, rm * D, true, D, D, B, kEpiF32Atomic, g + L.qkv_w, D, nullptr, 0,
+                          nullptr, nullptr, 0, 0, pick_splits(D, D, B), st));
+      }
       // layernorm_before + residual
       // dx of layer l's input == gradient of layer (l-1)'s output: its column sums are that layer's fc2 bias gradient
       TIC_TRY(layernorm_bwd(dh, D, x_in, D, mean1, rstd1, p32 + L.ln1_w, dx, D, M, D, dx, D, l > 0 ? dxb : nullptr, D,
