@@ -314,6 +314,39 @@ def run_ours(args):
                h2d_bytes_per_step=(x_host.numel() * 4 + y_host.numel() * 8) * world, d2h_bytes_per_step=4 * world,
                api="touhouimageclassification_b200.finetune.train_step(model, (x_host, y_host), FusedAdamW, CrossEntropyLoss)")
 
+    # ---- BASELINE config 3: ntrain's step with the train transform on the device. Pinned uint8 NHWC thumbnails (256x256,
+    # the reference's source size) -> H2D -> fused augmentation -> CutMix/MixUp + patchify -> engine step -> loss.item()
+    e2e_aug = None
+    if S <= 224:
+        from touhouimageclassification_b200.augment import GpuAugment
+        from touhouimageclassification_b200.ntrain import ViTLModule
+        mod = ViTLModule(WORKLOAD["num_labels"], False, "google/vit-base-patch16-224", 1e-5, 0.01, enable_mixup=True,
+                         fused_optimizer=True)
+        mod.vit = model                      # the module under test is the benchmarked one (no second ViT on the device)
+        aug = GpuAugment(seed=1234 + rank, size=S, recipe="full")
+        u8_host = torch.randint(0, 256, (B, 256, 256, 3), dtype=torch.uint8).pin_memory()
+        torch.manual_seed(99 + rank)         # CutMix / MixUp draws
+
+        def aug_step():
+            xi = u8_host.to(dev, non_blocking=True)
+            yi = y_host.to(dev, non_blocking=True)
+            return float(mod.fused_training_step((xi, yi), opt, grad_sync=trainer._grad_sync if world > 1 else None,
+                                                 world_size=world, augment=aug).item())
+
+        for _ in range(2):
+            aug_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            aug_step()
+        barrier()
+        aug_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / e2e_steps
+        e2e_aug = dict(value=PER_GPU_BATCH * world / (aug_ms / 1e3), unit="img/s", ms_per_step=aug_ms,
+                       h2d_bytes_per_step=(u8_host.numel() + y_host.numel() * 8) * world, d2h_bytes_per_step=4 * world,
+                       api="touhouimageclassification_b200.ntrain.ViTLModule.fused_training_step((uint8 NHWC 256x256, y), "
+                           "FusedAdamW, augment=GpuAugment(recipe='full')) with CutMix/MixUp")
+        del mod
+
     # ---- batched inference (BASELINE config 4: utils/filter + web serve path), per-GPU replica, device-resident inputs
     inference = None
     if not args.no_inference:
@@ -354,6 +387,8 @@ def run_ours(args):
         line = base_line(args, n_gpus=world)
         line.update(value=value, ms_per_step=ms_step, e2e=e2e, roofline=roofline, gpu_launches=int(launches),
                     clocks=clocks.summary(), loss=loss_val)
+        if e2e_aug is not None:
+            line["e2e_augmented"] = e2e_aug
         if inference is not None:
             line["inference"] = inference
         if world == 1 and not args.no_cpu_baseline:

@@ -180,6 +180,12 @@ TIC_API int tic_augment_sample_params(int64_t seed, int64_t first_sample, int B,
 TIC_API int tic_augment_patchify(const void* images_u8, int B, int H, int W, const int32_t* ints, const float* floats,
                                  int size, const float* mean3_host, const float* std3_host, void* patches_bf16,
                                  void* pixels_out_u8, void* stream);
+/* Same pipeline, same parameters, but yields what the reference's Dataset yields: the normalised fp32 tensor
+ * [B, 3, size, size] (ntrain.py:104-112 ends in ToTensor + Normalize), i.e. the input of the per-batch CutMix / MixUp
+ * (ntrain.py:45-46 -> tic_mix_patchify_f32). patches_bf16 is optional here (may be NULL). */
+TIC_API int tic_augment_tensor(const void* images_u8, int B, int H, int W, const int32_t* ints, const float* floats,
+                               int size, const float* mean3_host, const float* std3_host, float* tensor_out_f32,
+                               void* patches_bf16, void* stream);
 
 /* ---- whole-model engine ---------------------------------------------------------------------------
  * Stands where ViTForImageClassification.forward (modeling_vit.py:620-653) and its autograd backward

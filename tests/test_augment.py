@@ -164,6 +164,43 @@ def test_augmented_patches_feed_the_engine():
 
 
 @pytest.mark.gpu
+def test_augmented_tensor_is_totensor_normalize_of_the_augmented_pixels():
+    """GpuAugment.tensor == ToTensor + Normalize (ntrain.py:110-111) of the uint8 image the same draws produce, bit for
+    bit in fp32, and its bf16 patch rows are the ones the patch-row path writes."""
+    from touhouimageclassification_b200 import ops
+    from touhouimageclassification_b200.augment import GpuAugment, IMAGENET_MEAN, IMAGENET_STD
+    imgs = torch.from_numpy(smooth_images(5, 256, 256, 7)).cuda()
+    patches, pixels, _ = GpuAugment(seed=11)(imgs, first_sample=40, return_pixels=True)
+    t = GpuAugment(seed=11).tensor(imgs, first_sample=40)
+    assert t.shape == (5, 3, 224, 224) and t.dtype == torch.float32
+    # on the CPU, where the reference's transform runs (torch's CUDA kernels divide by a scalar through its reciprocal)
+    x = pixels.cpu().permute(0, 3, 1, 2).float().div(255.0)
+    mean = torch.tensor(IMAGENET_MEAN, dtype=torch.float32).view(1, 3, 1, 1)
+    std = torch.tensor(IMAGENET_STD, dtype=torch.float32).view(1, 3, 1, 1)
+    assert torch.equal(t.cpu(), x.sub(mean).div(std))
+    assert torch.equal(ops.patchify_f32(t), patches)
+
+
+@pytest.mark.gpu
+def test_fused_training_step_takes_uint8_thumbnails():
+    """ntrain's step with the train transform on the device: uint8 NHWC in, CutMix / MixUp, engine step, finite loss;
+    with mixing off the patch rows come straight from the augmentation kernel."""
+    from touhouimageclassification_b200.augment import GpuAugment
+    from touhouimageclassification_b200.ntrain import ViTLModule
+    torch.manual_seed(0)
+    imgs = torch.from_numpy(smooth_images(4, 256, 256, 5)).cuda()
+    y = torch.tensor([1, 0, 3, 2], device="cuda")
+    for mix in (True, False):
+        mod = ViTLModule(5, False, "google/vit-base-patch16-224", 1e-3, 0.01, enable_mixup=mix, fused_optimizer=True).cuda().train()
+        opt = mod.configure_optimizers()
+        before = mod.vit.classifier.weight.detach().clone()
+        loss = mod.fused_training_step((imgs, y), opt, augment=GpuAugment(seed=1))
+        assert torch.isfinite(loss) and not torch.equal(before, mod.vit.classifier.weight)
+        with pytest.raises(ValueError):
+            mod.fused_training_step((imgs, y), opt)
+
+
+@pytest.mark.gpu
 def test_inference_transform_on_gpu_matches_reference_recipe():
     """serve.preprocess_u8 == Resize((224,224)) -> ToTensor -> Normalize(dataset mean/std) (preprocess.py:73-77):
     bit-exact against the oracle's 'none' recipe, and within 1 LSB of torchvision's own uint8 resize."""

@@ -39,7 +39,7 @@ class GpuAugment:
         self._std = (ctypes.c_float * 3)(*[float(np.float32(s)) for s in std])
         self.samples_seen = 0
 
-    def __call__(self, images: torch.Tensor, first_sample: int = None, return_pixels: bool = False):
+    def _prepare(self, images: torch.Tensor, first_sample):
         if not images.is_cuda or images.dtype != torch.uint8 or images.dim() != 4 or images.shape[-1] != 3:
             raise ValueError("GpuAugment takes a CUDA uint8 NHWC batch [B, H, W, 3] (there is no CPU fallback)")
         images = images.contiguous()
@@ -51,6 +51,12 @@ class GpuAugment:
         dev = images.device
         ints_d = torch.from_numpy(ints).to(dev, non_blocking=True)
         floats_d = torch.from_numpy(floats).to(dev, non_blocking=True)
+        return images, ints, floats, ints_d, floats_d
+
+    def __call__(self, images: torch.Tensor, first_sample: int = None, return_pixels: bool = False):
+        images, ints, floats, ints_d, floats_d = self._prepare(images, first_sample)
+        B, H, W, _ = images.shape
+        dev = images.device
         G = self.size // 16
         patches = torch.empty((B * G * G, 768), dtype=torch.bfloat16, device=dev)
         pixels = torch.empty((B, self.size, self.size, 3), dtype=torch.uint8, device=dev) if return_pixels else None
@@ -61,3 +67,15 @@ class GpuAugment:
         if return_pixels:
             return patches, pixels, (ints, floats)
         return patches
+
+    def tensor(self, images: torch.Tensor, first_sample: int = None) -> torch.Tensor:
+        """The batch the reference's DataLoader would hand to ``training_step``: fp32 ``[B, 3, size, size]``, normalised
+        (ntrain.py:104-112 ends in ToTensor + Normalize) -- the input of the per-batch CutMix / MixUp (ntrain.py:45-46)."""
+        images, ints, floats, ints_d, floats_d = self._prepare(images, first_sample)
+        B, H, W, _ = images.shape
+        out = torch.empty((B, 3, self.size, self.size), dtype=torch.float32, device=images.device)
+        _lib.check(_lib.load().tic_augment_tensor(
+            c_void_p(images.data_ptr()), c_int(B), c_int(H), c_int(W), c_void_p(ints_d.data_ptr()),
+            c_void_p(floats_d.data_ptr()), c_int(self.size), self._mean, self._std, c_void_p(out.data_ptr()),
+            c_void_p(0), c_void_p(torch.cuda.current_stream().cuda_stream)))
+        return out

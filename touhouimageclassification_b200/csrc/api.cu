@@ -124,7 +124,14 @@ TIC_API int tic_augment_patchify(const void* images_u8, int B, int H, int W, con
                                  int size, const float* mean3_host, const float* std3_host, void* patches_bf16,
                                  void* pixels_out_u8, void* stream) {
   return augment_patchify(images_u8, B, H, W, ints, floats, size, mean3_host, std3_host, patches_bf16, pixels_out_u8,
-                          S(stream));
+                          nullptr, S(stream));
+}
+TIC_API int tic_augment_tensor(const void* images_u8, int B, int H, int W, const int32_t* ints, const float* floats,
+                               int size, const float* mean3_host, const float* std3_host, float* tensor_out_f32,
+                               void* patches_bf16, void* stream) {
+  if (tensor_out_f32 == nullptr) return set_error(kErrInvalidArg, "tic_augment_tensor: tensor_out_f32 is NULL");
+  return augment_patchify(images_u8, B, H, W, ints, floats, size, mean3_host, std3_host, patches_bf16, nullptr,
+                          tensor_out_f32, S(stream));
 }
 
 TIC_API int64_t tic_vit_param_arena_elems(const tic_vit_config* cfg) {

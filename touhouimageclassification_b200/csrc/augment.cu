@@ -41,7 +41,8 @@ __device__ __forceinline__ float clamp01(float x) { return fminf(fmaxf(x, 0.0f),
 __global__ void __launch_bounds__(AUG_THREADS, 1)
 augment_patchify_kernel(const unsigned char* __restrict__ images, int H, int W, const int* __restrict__ ints,
                         const float* __restrict__ floats, int size, float m0, float m1, float m2, float s0, float s1,
-                        float s2, __nv_bfloat16* __restrict__ patches, unsigned char* __restrict__ pixels_out) {
+                        float s2, __nv_bfloat16* __restrict__ patches, unsigned char* __restrict__ pixels_out,
+                        float* __restrict__ tensor_out) {
   extern __shared__ __align__(16) unsigned char aug_smem[];
   AugTables* tab = reinterpret_cast<AugTables*>(aug_smem);
   unsigned char* pix = aug_smem + ((sizeof(AugTables) + 15) / 16) * 16;  // planar [3][size*size]
@@ -215,6 +216,20 @@ augment_patchify_kernel(const unsigned char* __restrict__ images, int H, int W, 
   // ---- 5. ToTensor (/255), Normalize, bf16, patch rows with K ordered (c, py, px); 16-byte stores
   const int G = size / 16;
   const float mean_c[3] = {m0, m1, m2}, std_c[3] = {s0, s1, s2};
+  if (tensor_out != nullptr) {  // the fp32 [3, size, size] tensor the reference's Dataset yields (what CutMix / MixUp blend)
+    float* to = tensor_out + static_cast<long long>(b) * 3 * npix;
+    for (int e = tid; e < 3 * npix / 4; e += AUG_THREADS) {
+      const int c = (e * 4) / npix;  // npix is a multiple of 256: a group of four never straddles a plane
+      const unsigned int raw = *reinterpret_cast<const unsigned int*>(pix + e * 4);
+      float4 v;
+      v.x = __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(raw & 0xffu), 255.0f), mean_c[c]), std_c[c]);
+      v.y = __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>((raw >> 8) & 0xffu), 255.0f), mean_c[c]), std_c[c]);
+      v.z = __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>((raw >> 16) & 0xffu), 255.0f), mean_c[c]), std_c[c]);
+      v.w = __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(raw >> 24), 255.0f), mean_c[c]), std_c[c]);
+      *reinterpret_cast<float4*>(to + e * 4) = v;
+    }
+  }
+  if (patches == nullptr) return;
   __nv_bfloat16* out = patches + static_cast<long long>(b) * G * G * 768;
   for (int e = tid; e < G * G * 96; e += AUG_THREADS) {
     const int row = e / 96, chunk = e - row * 96;
@@ -328,10 +343,12 @@ int augment_sample_params(long long seed, long long first_sample, int B, int H, 
 
 int augment_patchify(const void* images_u8, int B, int H, int W, const int* ints_dev, const float* floats_dev, int size,
                      const float* mean3_host, const float* std3_host, void* patches_bf16, void* pixels_out_u8,
-                     cudaStream_t stream) {
+                     float* tensor_out_f32, cudaStream_t stream) {
   if (size % 16 != 0 || size > AUG_MAX_SIZE || size <= 0)
     return set_error(kErrUnsupported, "augment_patchify: output size %d (multiple of 16, <= %d)", size, AUG_MAX_SIZE);
   if (B <= 0) return kOk;
+  if (patches_bf16 == nullptr && tensor_out_f32 == nullptr)
+    return set_error(kErrInvalidArg, "augment_patchify: no output requested (patches and tensor are both NULL)");
   // tap tables hold at most AUG_MAX_TAPS taps: support = max(in/out, 1) must be <= 3.5
   if (H > 3 * size || W > 3 * size)
     return set_error(kErrUnsupported, "augment_patchify: source %dx%d is more than 3x the output size", H, W);
@@ -347,7 +364,7 @@ int augment_patchify(const void* images_u8, int B, int H, int W, const int* ints
   augment_patchify_kernel<<<B, AUG_THREADS, smem, stream>>>(
       reinterpret_cast<const unsigned char*>(images_u8), H, W, ints_dev, floats_dev, size, mean3_host[0], mean3_host[1],
       mean3_host[2], std3_host[0], std3_host[1], std3_host[2], reinterpret_cast<__nv_bfloat16*>(patches_bf16),
-      reinterpret_cast<unsigned char*>(pixels_out_u8));
+      reinterpret_cast<unsigned char*>(pixels_out_u8), tensor_out_f32);
   return check_launch("augment_patchify");
 }
 

@@ -72,7 +72,7 @@ int augment_sample_params(long long seed, long long first_sample, int B, int H, 
                           int* ints_host, float* floats_host);
 int augment_patchify(const void* images_u8, int B, int H, int W, const int* ints_dev, const float* floats_dev, int size,
                      const float* mean3_host, const float* std3_host, void* patches_bf16, void* pixels_out_u8,
-                     cudaStream_t stream);
+                     float* tensor_out_f32, cudaStream_t stream);
 
 // attention_tc.cu (tcgen05 / TMEM / TMA)
 // Nq (0 = N): only the first Nq tokens of every image act as queries (N <= 224 / 256 paths only); lse is [B, H, Nq].

@@ -87,10 +87,21 @@ class ViTLModule(_Base):
         self.log('train_loss', loss, prog_bar=True)
         return loss
 
-    def fused_training_step(self, batch, optimizer: FusedAdamW, grad_sync=None, world_size: int = 1):
-        """training_step + backward + optimizer step in one engine pass (manual-optimization fast path)."""
+    def fused_training_step(self, batch, optimizer: FusedAdamW, grad_sync=None, world_size: int = 1, augment=None):
+        """training_step + backward + optimizer step in one engine pass (manual-optimization fast path).
+
+        ``batch`` is what the reference's DataLoader yields (fp32 ``[B, 3, S, S]`` images, ntrain.py:43-44) or, with
+        ``augment`` (a :class:`~.augment.GpuAugment`), the raw uint8 NHWC thumbnails: the train transform of
+        ``AugmentedDataset.setup`` (ntrain.py:104-112) then runs on the device inside the step."""
         x, y = batch
         patches = None
+        if x.dtype == torch.uint8:
+            if augment is None:
+                raise ValueError("a uint8 batch needs augment=GpuAugment(...) (the reference's train transform)")
+            if self.enable_mixup:
+                x = augment.tensor(x)
+            else:  # no per-batch blend: the augmentation kernel writes the bf16 patch rows directly
+                patches, x = augment(x), None
         if self.enable_mixup:  # the mixed image is never materialised: the kernel writes the bf16 patch rows directly
             _, y, patches = cutmix_or_mixup(x, y, self.num_classes, want_pixels=False, want_patches=True)
             x = None
