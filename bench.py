@@ -222,6 +222,8 @@ def run_ours(args):
     opt = FusedAdamW(model, lr=1e-5, weight_decay=0.01)
     trainer = DataParallelTrainer(model, opt, bucket_mb=args.bucket_mb)
     trainer.broadcast_parameters(0)
+    if args.diag_no_allreduce:
+        trainer.bucketer.all_reduce = lambda flat, begin, end: None
     B, S = PER_GPU_BATCH, WORKLOAD["image_size"]
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     x_dev = torch.randn(B, 3, S, S, device=dev, generator=g)
@@ -387,6 +389,8 @@ def run_ours(args):
         line = base_line(args, n_gpus=world)
         line.update(value=value, ms_per_step=ms_step, e2e=e2e, roofline=roofline, gpu_launches=int(launches),
                     clocks=clocks.summary(), loss=loss_val)
+        if args.diag_no_allreduce:
+            line["invalid"] = "diagnostic run without the gradient all-reduce"
         if e2e_aug is not None:
             line["e2e_augmented"] = e2e_aug
         if inference is not None:
@@ -426,6 +430,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--bucket-mb", type=float, default=96.0, help="gradient all-reduce bucket size (N > 1)")
+    ap.add_argument("--diag-no-allreduce", action="store_true",
+                    help="DIAGNOSTIC ONLY (N > 1): skip the gradient all-reduce to size its cost; the line is marked invalid")
     ap.add_argument("--no-inference", action="store_true", help="skip the batched-inference sweep after the training bench")
     ap.add_argument("--workload", default="vitl224", choices=sorted(WORKLOADS),
                     help="vitl224 = the BASELINE.json headline (default); vitb224 / vitl384 = BASELINE configs 2 and 5")

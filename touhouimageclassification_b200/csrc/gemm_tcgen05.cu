@@ -20,6 +20,8 @@
 //   wgrad    dW = dY^T X : A = dY (MN-major)  B = X  (MN-major), split over the token dimension
 #include "tic_internal.cuh"
 
+#include <cstdlib>
+
 #include <type_traits>
 
 namespace tic {
@@ -31,6 +33,7 @@ constexpr int BN = 256;
 constexpr int BK = 64;
 constexpr int UMMA_K = 16;
 constexpr int ACC_STAGES = 2;
+constexpr int CLC_STAGES = 4;  // ring of cluster-launch-control responses (tile hand-outs in flight)
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
 // Epilogue warps per CTA: 8 (two per TMEM lane quadrant) everywhere except the GELU forward epilogue, whose ~24
 // instructions per element (value + derivative) need more issue slots than two warps per SM sub-partition deliver inside
@@ -50,7 +53,7 @@ struct Cfg {
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int STAGES = NCTA == 2 ? (NEPI > 8 ? 5 : 6) : 4;
   static constexpr int TILE_M = BM * NCTA;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + NEPI * EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + NEPI * EPI_STAGE_BYTES + 1024 /*align*/ + 512 /*barriers*/;
 };
 
 
@@ -67,6 +70,7 @@ struct GemmParams {
   int aux_int;  // kEpiF32PosEmbed: patches per image (P)
   float* colsum;  // kEpiBf16 / kEpiBf16DGelu: optional, accumulates column sums of the bf16 output (a bias gradient)
   int exact;      // fp32 verification mode: kEpiF32Resid / kEpiF32PosEmbed add without the bf16 rounding of autocast
+  int dynamic;    // 1: one cluster per tile in the grid, running clusters take over not-yet-started ones (cluster launch control)
 };
 
 template <bool A_MN, bool B_MN, int EPI, int NCTA>
@@ -94,7 +98,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   uint64_t* empty_bar = bars + STAGES;            // [STAGES]   MMA -> TMA
   uint64_t* tmem_full_bar = bars + 2 * STAGES;    // [ACC_STAGES] MMA -> epilogue
   uint64_t* tmem_empty_bar = tmem_full_bar + ACC_STAGES;  // [ACC_STAGES] epilogue -> MMA
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + ACC_STAGES);
+  uint64_t* clc_full = tmem_empty_bar + ACC_STAGES;       // [CLC_STAGES] hardware -> every role, per CTA
+  uint64_t* clc_empty = clc_full + CLC_STAGES;            // [CLC_STAGES] every role (both CTAs) -> the leader's scheduler
+  uint4* clc_resp = reinterpret_cast<uint4*>(bars + 32);  // [CLC_STAGES] 16-byte responses (256 B into the region)
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(clc_resp + CLC_STAGES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -121,6 +128,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         mbar_init(&tmem_full_bar[i], 1);
         mbar_init(&tmem_empty_bar[i], NUM_EPI_WARPS * NCTA);
       }
+      for (int i = 0; i < CLC_STAGES; ++i) {
+        mbar_init(&clc_full[i], 1);
+        // readers of a response: the leader's MMA thread, the peer's TMA thread, every epilogue warp of the cluster
+        mbar_init(&clc_empty[i], NUM_EPI_WARPS * NCTA + 1 + (NCTA - 1));
+      }
       fence_mbar_init();
     }
     __syncwarp();
@@ -133,6 +145,57 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
 
+  // ---- tile sequence of this worker (a CTA or a CTA pair).
+  // Static: tiles worker, worker + num_workers, ... of a grid sized to the machine.
+  // Dynamic (p.dynamic): the grid holds one cluster per tile; a running cluster starts with its own tile and then asks
+  // the hardware (cluster launch control) to cancel a cluster that has not started and processes that one's tile, so
+  // the tiles spread over whatever SMs are actually free (e.g. while a NCCL kernel holds some) instead of waiting for
+  // a fixed owner. The leader's TMA thread issues request i before loading tile i; every role reads response i after
+  // tile i and releases the slot.
+  auto next_tile = [&](int tile, int& qi, bool release) -> int {
+    if (!p.dynamic) {
+      const int t = tile + num_workers;
+      return t < total_tiles ? t : -1;
+    }
+    const int slot = qi % CLC_STAGES;
+    const uint32_t ph = static_cast<uint32_t>(qi / CLC_STAGES) & 1u;
+    ++qi;
+    mbar_wait(&clc_full[slot], ph);
+    const int x = clc_decode(&clc_resp[slot]);
+    if (release) {
+      fence_proxy_async();  // this read happens before the next asynchronous write of the slot
+      if constexpr (NCTA == 2) mbar_arrive_cluster(&clc_empty[slot], 0);
+      else mbar_arrive(&clc_empty[slot]);
+    }
+    return x < 0 ? -1 : x / NCTA;
+  };
+  auto request_tile = [&](int q) {  // leader's TMA thread only
+    const int slot = q % CLC_STAGES;
+    const uint32_t ph = static_cast<uint32_t>(q / CLC_STAGES) & 1u;
+    mbar_wait(&clc_empty[slot], ph ^ 1);
+    mbar_arrive_expect_tx(&clc_full[slot], 16);
+    if constexpr (NCTA == 2) {
+      mbar_arrive_expect_tx_cluster(&clc_full[slot], 16, 1);
+      clc_try_cancel_multicast(&clc_resp[slot], &clc_full[slot]);
+    } else {
+      clc_try_cancel(&clc_resp[slot], &clc_full[slot]);
+    }
+  };
+
+  auto next_tile_warp = [&](int tile, int& qi) -> int {  // whole-warp form: every lane reads, lane 0 releases
+    const int t = next_tile(tile, qi, false);
+    if (p.dynamic) {
+      __syncwarp();
+      if (lane == 0) {
+        const int slot = (qi - 1) % CLC_STAGES;
+        fence_proxy_async();
+        if constexpr (NCTA == 2) mbar_arrive_cluster(&clc_empty[slot], 0);
+        else mbar_arrive(&clc_empty[slot]);
+      }
+    }
+    return t;
+  };
+
   if (warp == kTmaWarp) {
     // ------------------------------------------------------------------ TMA producer
     if (elect_one()) {
@@ -142,7 +205,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         if constexpr (NCTA == 2) tma_load_2d_2cta(dst, map, bar, c0, c1);
         else tma_load_2d(dst, map, bar, c0, c1);
       };
-      for (int tile = worker; tile < total_tiles; tile += num_workers) {
+      int qi = 0;
+      for (int tile = worker; tile >= 0; tile = next_tile(tile, qi, cta_rank != 0)) {
+        if (p.dynamic && cta_rank == 0) request_tile(qi);
         const int split = tile / tiles_per_split;
         const int rem = tile - split * tiles_per_split;
         const int m_idx = (rem / n_blocks) * C::TILE_M + static_cast<int>(cta_rank) * BM;        // this CTA's A rows
@@ -188,7 +253,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       uint32_t phase = 0;
       int acc_stage = 0;
       uint32_t acc_phase = 0;
-      for (int tile = worker; tile < total_tiles; tile += num_workers) {
+      int qi = 0;
+      for (int tile = worker; tile >= 0; tile = next_tile(tile, qi, true)) {
         const int split = tile / tiles_per_split;
         const int kb_begin = split * k_blocks_per_split;
         const int kb_end = min(k_blocks_total, kb_begin + k_blocks_per_split);
@@ -231,7 +297,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     const int ch = lane & 7;        // phase B: 16-byte chunk (4 fp32 columns)
     int acc_stage = 0;
     uint32_t acc_phase = 0;
-    for (int tile = worker; tile < total_tiles; tile += num_workers) {
+    int qi = 0;
+    for (int tile = worker; tile >= 0; tile = next_tile_warp(tile, qi)) {
       const int split = tile / tiles_per_split;
       const int rem = tile - split * tiles_per_split;
       const int m_idx = (rem / n_blocks) * C::TILE_M + static_cast<int>(cta_rank) * BM;  // this CTA's accumulator rows
@@ -436,7 +503,12 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cu
   const int m_blocks = (p.M + C::TILE_M - 1) / C::TILE_M, n_blocks = (p.N + BN - 1) / BN;
   const int total = m_blocks * n_blocks * p.splits;
   const int max_workers = num_sms() / kNcta;
-  const int workers = total < max_workers ? total : max_workers;
+  // dynamic: one cluster per tile, the running ones take over the rest (see the kernel); TIC_GEMM_STATIC=1 keeps the
+  // fixed persistent grid (development A/B)
+  static const bool force_static = std::getenv("TIC_GEMM_STATIC") != nullptr;
+  GemmParams pl = p;
+  pl.dynamic = force_static ? 0 : 1;
+  const int workers = (pl.dynamic || total < max_workers) ? total : max_workers;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(workers * kNcta);
   cfg.blockDim = dim3((epi_warps<EPI>() + 2) * 32);
@@ -449,7 +521,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cu
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, pl);
   if (e != cudaSuccess) return set_error(kErrCuda, "gemm: cudaLaunchKernelEx: %s", cudaGetErrorString(e));
   return check_launch("gemm_bf16_tcgen05");
 }

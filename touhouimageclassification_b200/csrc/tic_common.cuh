@@ -311,6 +311,49 @@ TIC_DEVINL void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
       "}\n" ::"r"(smem_u32(bar)), "r"(cta)
       : "memory");
 }
+TIC_DEVINL void mbar_arrive_expect_tx_cluster(uint64_t* bar, uint32_t bytes, uint32_t cta) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 remote;\n\t"
+      "mapa.shared::cluster.u32 remote, %0, %1;\n\t"
+      "mbarrier.arrive.expect_tx.shared::cluster.b64 _, [remote], %2;\n\t"
+      "}\n" ::"r"(smem_u32(bar)), "r"(cta), "r"(bytes)
+      : "memory");
+}
+
+// ---- cluster launch control (sm_100): a running cluster asks the hardware to cancel a cluster of the same grid that has
+// not started yet and takes over its work. The 16-byte response lands asynchronously in shared memory (at the same
+// offset in EVERY CTA of the cluster for the multicast form) and completes 16 transaction bytes on the mbarrier.
+TIC_DEVINL void clc_try_cancel_multicast(void* response16, uint64_t* bar) {
+  asm volatile(
+      "clusterlaunchcontrol.try_cancel.async.shared::cta.mbarrier::complete_tx::bytes.multicast::cluster::all.b128 [%0], [%1];"
+      ::"r"(smem_u32(response16)), "r"(smem_u32(bar))
+      : "memory");
+}
+TIC_DEVINL void clc_try_cancel(void* response16, uint64_t* bar) {
+  asm volatile("clusterlaunchcontrol.try_cancel.async.shared::cta.mbarrier::complete_tx::bytes.b128 [%0], [%1];"
+               ::"r"(smem_u32(response16)), "r"(smem_u32(bar))
+               : "memory");
+}
+// Decodes a response: returns blockIdx.x of the cancelled cluster's first CTA, or -1 when nothing was left to cancel.
+TIC_DEVINL int clc_decode(const void* response16) {
+  uint32_t x, ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p1;\n\t"
+      ".reg .b128 resp;\n\t"
+      "ld.shared.b128 resp, [%2];\n\t"
+      "clusterlaunchcontrol.query_cancel.is_canceled.pred.b128 p1, resp;\n\t"
+      "selp.u32 %1, 1, 0, p1;\n\t"
+      "mov.u32 %0, 0;\n\t"
+      "@p1 clusterlaunchcontrol.query_cancel.get_first_ctaid.v4.b32.b128 {%0, _, _, _}, resp;\n\t"
+      "}\n"
+      : "=r"(x), "=r"(ok)
+      : "r"(smem_u32(response16))
+      : "memory");
+  return ok ? static_cast<int>(x) : -1;
+}
+
 TIC_DEVINL void tma_load_2d_2cta(void* smem_dst, const void* desc, uint64_t* bar, int32_t c0, int32_t c1) {
   // executed by both CTAs of the pair; the transaction bytes are credited to the leader's barrier
   asm volatile(
