@@ -281,10 +281,24 @@ def run_ours(args):
     peak = peaks["bf16_tflops_sustained"]  # kernel timed inside a long step -> sustained figure
     achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else None
     step_flops = 3 * flops_per_image_forward(WORKLOAD) * PER_GPU_BATCH
+    # DRAM traffic per GEMM launch: from the committed ncu launch list of this command (dram__bytes_read + _write summed
+    # over every GEMM launch / launches); algorithmic bytes per launch from the same operand / output sizes the FLOPs use
+    traffic = traffic_src = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_launches_v3_summary.json")) as f:
+            traffic = float(json.load(f)["gemm"]["dram_bytes_per_launch"])
+            traffic_src = "profiles/r01_launches_v3_summary.json (ncu, mean over the GEMM launches of ~2 steps, vitl224)"
+    except Exception:
+        pass
+    if WORKLOAD_NAME != WORKLOADS["vitl224"][3]:
+        traffic = traffic_src = None
+    gemm_bytes = sum(v["bytes"] for v in gemm)
     roofline = dict(bound="tensor", kernel="gemm_bf16_tcgen05_kernel (all GEMM launches of one step)",
                     achieved=achieved, peak=peak, unit="TFLOP/s", frac=(achieved / peak if achieved else None),
                     peak_source=f"{peaks['source']} bf16_tflops_sustained (burst {peaks['bf16_tflops']})",
-                    traffic=None, launches_per_step=gemm_launches, kernel_ms_per_step=gemm_ms,
+                    traffic=traffic, traffic_unit="bytes per launch", traffic_source=traffic_src,
+                    algorithmic_bytes_per_launch=(gemm_bytes / gemm_launches if gemm_launches else None),
+                    launches_per_step=gemm_launches, kernel_ms_per_step=gemm_ms,
                     kernel_share_of_step=gemm_ms / prof_ms if prof_ms else None,
                     step_achieved=step_flops / (ms_step / 1e3) / 1e12,
                     step_frac_of_burst=step_flops / (ms_step / 1e3) / 1e12 / peaks["bf16_tflops"],
