@@ -5,10 +5,13 @@
 // the output is written as bf16 (the operand dtype of the GEMM that consumes it) and/or fp32.
 #include "tic_internal.cuh"
 
+#include <cstdlib>
+
 namespace tic {
 namespace {
 
 constexpr int LN_WARPS = 8;
+constexpr int LN_CLC_STAGES = 4;  // ring of cluster-launch-control responses (backward)
 
 // One warp per row; a lane owns float4 chunks lane, lane + 32, ... (VEC chunks, D = VEC * 128).
 template <int VEC>
@@ -72,7 +75,7 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long lddy, const float*
               const float* __restrict__ mean_in, const float* __restrict__ rstd_in, const float* __restrict__ gamma,
               const float* dres, long long lddres, int rows, float* dx, long long lddx,
               __nv_bfloat16* __restrict__ dx_bf16, long long lddxb, float* __restrict__ dgamma,
-              float* __restrict__ dbeta, float* __restrict__ dxsum) {
+              float* __restrict__ dbeta, float* __restrict__ dxsum, int dynamic, int chunk_rows) {
   constexpr int D = VEC * 128;
   extern __shared__ float4 ln_smem[];
   float4* sg = ln_smem;                           // [LN_WARPS][VEC * 32] dgamma partials
@@ -89,7 +92,34 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long lddy, const float*
     my_c[lane + 32 * i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   const float4* g4 = reinterpret_cast<const float4*>(gamma);
-  for (int row = blockIdx.x * LN_WARPS + warp; row < rows; row += gridDim.x * LN_WARPS) {
+  // Work is handed out in chunks of chunk_rows rows. Static: chunks blockIdx.x, blockIdx.x + gridDim.x, ...
+  // Dynamic: the grid holds one CTA per chunk and a running CTA takes over CTAs that have not started (cluster launch
+  // control), so the per-CTA accumulators stay few while the rows spread over whatever SMs are free (a NCCL kernel
+  // overlapping the backward may hold some). Warp 0 requests chunk n+1 before working on chunk n; the warps run
+  // independently and meet only through the response ring.
+  __shared__ __align__(16) uint4 clc_resp[LN_CLC_STAGES];
+  __shared__ __align__(8) uint64_t clc_full[LN_CLC_STAGES], clc_empty[LN_CLC_STAGES];
+  const int num_chunks = (rows + chunk_rows - 1) / chunk_rows;
+  if (dynamic) {
+    if (threadIdx.x == 0) {
+      for (int i = 0; i < LN_CLC_STAGES; ++i) {
+        mbar_init(&clc_full[i], 1);
+        mbar_init(&clc_empty[i], LN_WARPS);
+      }
+      fence_mbar_init();
+    }
+    __syncthreads();
+  }
+  int qi = 0;
+  for (int chunk = blockIdx.x; chunk >= 0 && chunk < num_chunks;) {
+    if (dynamic && threadIdx.x == 0) {  // request the chunk after this one
+      const int slot = qi % LN_CLC_STAGES;
+      mbar_wait(&clc_empty[slot], ((qi / LN_CLC_STAGES) & 1) ^ 1);
+      mbar_arrive_expect_tx(&clc_full[slot], 16);
+      clc_try_cancel(&clc_resp[slot], &clc_full[slot]);
+    }
+    const int row_end = min(rows, (chunk + 1) * chunk_rows);
+    for (int row = chunk * chunk_rows + warp; row < row_end; row += LN_WARPS) {
     const float mean = mean_in[row], rstd = rstd_in[row];
     const float4* xr = reinterpret_cast<const float4*>(x + static_cast<long long>(row) * ldx);
     const uint2* dyr = reinterpret_cast<const uint2*>(dy + static_cast<long long>(row) * lddy);
@@ -152,6 +182,20 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long lddy, const float*
         }
       }
     }
+    }
+    if (dynamic) {
+      const int slot = qi % LN_CLC_STAGES;
+      mbar_wait(&clc_full[slot], (qi / LN_CLC_STAGES) & 1);
+      chunk = clc_decode(&clc_resp[slot]);
+      ++qi;
+      __syncwarp();
+      if (lane == 0) {
+        fence_proxy_async();
+        mbar_arrive(&clc_empty[slot]);
+      }
+    } else {
+      chunk += gridDim.x;
+    }
   }
   __syncthreads();
   for (int c = threadIdx.x; c < VEC * 32; c += LN_WARPS * 32) {
@@ -211,9 +255,12 @@ int layernorm_bwd(const void* dy_bf16, long long lddy, const float* x, long long
   if (D % 128 != 0) return set_error(kErrUnsupported, "layernorm: D=%d must be a multiple of 128", D);
   if (dxsum != nullptr && dx_bf16 == nullptr)
     return set_error(kErrInvalidArg, "layernorm_bwd: dxsum needs the bf16 dx output");
-  int grid = (rows + LN_WARPS - 1) / LN_WARPS;
+  static const bool force_static = std::getenv("TIC_LN_STATIC") != nullptr;  // development A/B
+  const int dynamic = force_static ? 0 : 1;
+  const int chunk_rows = dynamic ? 8 * LN_WARPS : LN_WARPS;  // dynamic: 8 rows per warp between two hand-outs
+  int grid = (rows + chunk_rows - 1) / chunk_rows;  // dynamic: one CTA per chunk; running CTAs take over the rest
   const int max_grid = 148 * 2;
-  if (grid > max_grid) grid = max_grid;
+  if (!dynamic && grid > max_grid) grid = max_grid;
   ProfScope prof("layernorm_bwd", 0.0, static_cast<double>(rows) * D * (2 + 4 + (dres ? 4 : 0) + 4 + (dx_bf16 ? 2 : 0)), stream);
   auto* dyb = reinterpret_cast<const __nv_bfloat16*>(dy_bf16);
   auto* dxb = reinterpret_cast<__nv_bfloat16*>(dx_bf16);
@@ -226,7 +273,8 @@ int layernorm_bwd(const void* dy_bf16, long long lddy, const float* x, long long
       attr_set = true;                                                                                            \
     }                                                                                                             \
     ln_bwd_kernel<V><<<grid, LN_WARPS * 32, smem, stream>>>(dyb, lddy, x, ldx, mean, rstd, gamma, dres, lddres, rows, \
-                                                            dx, lddx, dxb, lddxb, dgamma, dbeta, dxsum);          \
+                                                            dx, lddx, dxb, lddxb, dgamma, dbeta, dxsum, dynamic, \
+                                                            chunk_rows);                                          \
     break;                                                                                                        \
   }
   switch (D / 128) {
