@@ -303,17 +303,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       const int rem = tile - split * tiles_per_split;
       const int m_idx = (rem / n_blocks) * C::TILE_M + static_cast<int>(cta_rank) * BM;  // this CTA's accumulator rows
       const int n_idx = (rem % n_blocks) * BN;
-      mbar_wait(&tmem_full_bar[acc_stage], acc_phase);
-      tc_fence_after();
       const int row_base = m_idx + quad * 32;
-#pragma unroll 1
-      for (int c = part; c < BN / 32; c += kParts) {
-        const int col0 = n_idx + c * 32;
-        const int col = col0 + ch * 4;
-        // Issue this chunk's coalesced auxiliary loads (residual / pre-activation / pos-emb rows) before the
-        // TMEM load so that their latency overlaps phase A.
-        float4 auxf[8];
-        uint2 auxh[8];
+      // The auxiliary operand of a 32-column chunk (residual / GELU' / pos-emb rows): coalesced loads, one chunk AHEAD of
+      // the chunk being processed (the first one before the accumulator is even complete), so that their DRAM latency
+      // hides under the previous chunk instead of stalling every chunk -- the K = 1024 residual GEMMs were bound by
+      // exactly that stall (tensor pipe 49 % active under ncu).
+      auto load_aux = [&](int c, float4 (&auxf)[8], uint2 (&auxh)[8]) {
+        const int col = n_idx + c * 32 + ch * 4;
         if constexpr (EPI == kEpiF32Resid || EPI == kEpiF32PosEmbed || EPI == kEpiBf16DGelu) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -333,6 +329,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             }
           }
         }
+      };
+      auto do_chunk = [&](int c, float4 (&auxf)[8], uint2 (&auxh)[8]) {
+        const int col0 = n_idx + c * 32;
+        const int col = col0 + ch * 4;
+        (void)col0;
         {
           uint32_t r[32];
           const uint32_t taddr = tmem_base + acc_stage * BN + c * 32 + (static_cast<uint32_t>(quad * 32) << 16);
@@ -454,6 +455,21 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           }
         }
         __syncwarp();
+      };
+      float4 fa[8], fb[8];
+      uint2 ha[8], hb[8];
+      load_aux(part, fa, ha);
+      mbar_wait(&tmem_full_bar[acc_stage], acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = part; c < BN / 32; c += 2 * kParts) {
+        const int c1 = c + kParts, c2 = c + 2 * kParts;
+        if (c1 < BN / 32) load_aux(c1, fb, hb);
+        do_chunk(c, fa, ha);
+        if (c1 < BN / 32) {
+          if (c2 < BN / 32) load_aux(c2, fa, ha);
+          do_chunk(c1, fb, hb);
+        }
       }
       // All TMEM reads of this warp have completed (wait::ld above): hand the accumulator stage back.
       tc_fence_before();
