@@ -31,8 +31,8 @@ def fused_train_step(model: ViTForImageClassification, optimizer: FusedAdamW, in
                      patches=None, grad_sync=None, world_size: int = 1) -> torch.Tensor:
     """forward -> softmax-CE (hard or soft targets) -> backward -> AdamW, all on the engine. Returns loss[1] (device).
 
-    ``grad_sync(model, stage_begin, stage_end)`` -- optional hook used by the data-parallel wrapper to launch the
-    bucketed gradient all-reduce as backward stages complete.
+    ``grad_sync(model, dlogits, batch, head_only)`` -- the data-parallel wrapper's schedule (backward stage by stage,
+    bucketed gradient all-reduce, AdamW per bucket); defaults to the same schedule without the exchange.
     """
     batch = inputs.shape[0] if inputs is not None else patches.shape[0] // ((model.config.image_size // 16) ** 2)
     logits = model.engine_forward(inputs, patches=patches, training=True)
@@ -42,13 +42,22 @@ def fused_train_step(model: ViTForImageClassification, optimizer: FusedAdamW, in
     optimizer.arena_clean = False
     params = model._params_in_order()
     head_only = not any(p.requires_grad for p in params[:-2])
-    if grad_sync is None:
-        model.engine_backward(dlogits, batch, head_only=head_only)
-    else:
-        grad_sync(model, dlogits, batch, head_only)
     optimizer.grads_in_arena = True
-    optimizer.step()
+    if grad_sync is None:  # single process: same bucketed schedule, no exchange
+        grad_sync = _local_schedule(model, optimizer)
+    # runs the backward stage by stage; as each bucket of gradients becomes final (after its all-reduce when there is
+    # one) AdamW is applied to that slice on a side stream, under the backward of the earlier layers
+    grad_sync(model, dlogits, batch, head_only)
     return loss
+
+
+def _local_schedule(model, optimizer):
+    sched = getattr(optimizer, "_local_schedule", None)
+    if sched is None or sched.model is not model:
+        from .parallel import DataParallelTrainer
+        sched = DataParallelTrainer(model, optimizer, local=True)
+        optimizer._local_schedule = sched
+    return sched._grad_sync
 
 
 def train_step(model, data, optimizer, criterion, scaler=None, scheduler=None):

@@ -103,6 +103,38 @@ class FusedAdamW(torch.optim.Optimizer):
                 elif p.grad.data_ptr() != v.data_ptr():
                     v.copy_(p.grad)
 
+    # The update can be applied slice by slice (the arena is flat and AdamW is elementwise): the train step runs it for
+    # each gradient bucket on a side stream as soon as that bucket's gradients are final, in the shadow of the backward
+    # of the earlier layers. begin_step / step_range / end_step are the three parts of step().
+    @torch.no_grad()
+    def begin_step(self):
+        self._ensure_state()
+        self._step += 1
+        if self.model._shadow is None:
+            self.model.refresh_shadow(force=True)
+
+    @torch.no_grad()
+    def step_range(self, begin: int, end: int, grad_scale: float = 1.0):
+        """AdamW over the trainable part of arena elements [begin, end) on the current stream."""
+        model = self.model
+        group = self.param_groups[0]
+        g = model.grad_arena()
+        b1, b2 = group["betas"]
+        for ra, rb in self._ranges:
+            a, b = max(begin, ra), min(end, rb)
+            if a < b:
+                ops.adamw_step(model._arena[a:b], g[a:b], self._m[a:b], self._v[a:b], model._shadow[a:b],
+                               float(group["lr"]), b1, b2, group["eps"], group["weight_decay"], self._step, grad_scale)
+
+    @torch.no_grad()
+    def end_step(self):
+        for st in self.state.values():
+            if "step" in st:
+                st["step"].fill_(float(self._step))
+        self.model.mark_shadow_fresh()
+        self.grads_in_arena = False
+        self.arena_clean = False
+
     @torch.no_grad()
     def step(self, closure=None, grad_scale: float = 1.0):
         loss = None
@@ -112,22 +144,9 @@ class FusedAdamW(torch.optim.Optimizer):
         self._ensure_state()
         if not self.grads_in_arena:
             self._gather_grads()
-        group = self.param_groups[0]
-        self._step += 1
-        model = self.model
-        if model._shadow is None:
-            model.refresh_shadow(force=True)
-        g = model.grad_arena()
-        b1, b2 = group["betas"]
-        for a, b in self._ranges:
-            ops.adamw_step(model._arena[a:b], g[a:b], self._m[a:b], self._v[a:b], model._shadow[a:b], float(group["lr"]),
-                           b1, b2, group["eps"], group["weight_decay"], self._step, grad_scale)
-        for st in self.state.values():
-            if "step" in st:
-                st["step"].fill_(float(self._step))
-        model.mark_shadow_fresh()
-        self.grads_in_arena = False
-        self.arena_clean = False
+        self.begin_step()
+        self.step_range(0, self.model._arena.numel(), grad_scale)
+        self.end_step()
         return loss
 
     def load_state_dict(self, state_dict):

@@ -10,6 +10,7 @@ the global-batch mean and every rank applies the identical AdamW update (paramet
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import List, Optional, Tuple
 
 import torch
@@ -68,12 +69,15 @@ class DataParallelTrainer:
     """Fused train step + bucketed gradient all-reduce overlapped with backward."""
 
     def __init__(self, model: ViTForImageClassification, optimizer: FusedAdamW, process_group=None,
-                 bucket_mb: float = 96.0):
+                 bucket_mb: float = 96.0, local: bool = False):
         self.model, self.optimizer = model, optimizer
-        self.bucketer = GradBucketer(process_group)
-        self.world_size = self.bucketer.world_size
+        self.bucketer = GradBucketer(process_group) if not local else None
+        self.world_size = self.bucketer.world_size if self.bucketer is not None else 1
         self.buckets = make_buckets(stage_grad_ranges(model), int(bucket_mb * (1 << 20) / 4))
-        self.comm_stream = torch.cuda.Stream() if torch.cuda.is_available() and self.world_size > 1 else None
+        # side stream: the all-reduce of a bucket (N > 1) and then AdamW over that bucket run here while the main stream
+        # continues with the backward of the earlier layers
+        self.comm_stream = torch.cuda.Stream() if torch.cuda.is_available() else None
+        self.update_at_end = os.environ.get("TIC_ADAMW_AT_END") is not None  # development A/B: one AdamW launch after backward
 
     def broadcast_parameters(self, src: int = 0):
         """Make every replica start from rank ``src``'s weights."""
@@ -85,20 +89,32 @@ class DataParallelTrainer:
 
     def _grad_sync(self, model, dlogits, batch, head_only):
         g = model.grad_arena()
-        main = torch.cuda.current_stream()
+        opt = self.optimizer
+        opt.begin_step()
+        main = torch.cuda.current_stream() if self.comm_stream is not None else None
         if self.comm_stream is not None:
-            self.comm_stream.wait_stream(main)  # the arena was zeroed on the main stream
+            self.comm_stream.wait_stream(main)  # the arena was zeroed (and the forward ran) on the main stream
         for (s0, s1, b, e) in self.buckets:
             model.engine_backward(dlogits, batch, head_only=head_only, stage_begin=s0, stage_end=s1)
-            if self.comm_stream is None:
+            if self.comm_stream is None:  # CPU tests (gloo): in order
+                if self.bucketer is not None:
+                    self.bucketer.all_reduce(g, b, e)
                 continue
             ev = torch.cuda.Event()
             ev.record(main)
             with torch.cuda.stream(self.comm_stream):
                 self.comm_stream.wait_event(ev)
-                self.bucketer.all_reduce(g, b, e)
+                if self.bucketer is not None:
+                    self.bucketer.all_reduce(g, b, e)
+                # the bucket's gradients are final and its layers' backward is over: nobody reads these weights again
+                # in this step, so the update (fp32 parameters, moments, bf16 shadow) can run under the rest of backward
+                if not self.update_at_end:
+                    opt.step_range(b, e)
         if self.comm_stream is not None:
             main.wait_stream(self.comm_stream)
+        if self.comm_stream is None or self.update_at_end:
+            opt.step_range(0, g.numel())
+        opt.end_step()
 
     def step(self, inputs=None, target=None, patches=None) -> torch.Tensor:
         return fused_train_step(self.model, self.optimizer, inputs, target, patches=patches,
