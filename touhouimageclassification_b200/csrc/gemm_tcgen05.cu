@@ -6,12 +6,15 @@
 // intermediate :290-299, output :305-312, patch projection :151-167) and their autograd
 // backward GEMMs (cuBLASLt in the reference's stack).
 //
-// One persistent CTA per SM, 10 warps:
+// One CTA pair (cluster of 2, tcgen05 cta_group::2) per two SMs computes 256 x 256 tiles; 10 warps per CTA (14 for the
+// GELU epilogue):
 //   warps 0-7  epilogue   (TMEM -> registers -> fused math -> global), 2 warps per TMEM lane quadrant
-//   warp  8    TMA producer (one elected lane)
-//   warp  9    MMA issuer  (one elected lane) + TMEM allocator
-// Three mbarrier pipelines: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue);
+//   warp  8    TMA producer (one elected lane) + tile scheduler of the pair (leader CTA)
+//   warp  9    MMA issuer  (one elected lane, leader CTA) + TMEM allocator
+// mbarrier pipelines: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue), tile hand-out full/empty;
 // two 256-column accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1.
+// Tiles are handed out by the hardware (cluster launch control): the grid holds one pair per tile, the pairs that run
+// cancel not-yet-started ones and take their tiles, so the kernel is persistent without a fixed tile -> SM mapping.
 //
 // Operand majors (template): K-major = reduction dimension contiguous in memory,
 // MN-major = the M (or N) dimension contiguous. The three GEMMs of a Linear layer map to
