@@ -219,7 +219,8 @@ def test_patchify_is_exact_and_colsum():
     assert rel(ops.colsum_bf16(dy), dy.float().sum(0)) < 1e-5
 
 
-@pytest.mark.parametrize("B,N,H,Nq", [(3, 197, 4, 1), (2, 197, 2, 70), (2, 64, 2, 1), (2, 130, 2, 129), (4, 197, 16, 1)])
+@pytest.mark.parametrize("B,N,H,Nq", [(3, 197, 4, 1), (2, 197, 2, 70), (2, 64, 2, 1), (2, 130, 2, 129), (4, 197, 16, 1),
+                                      (2, 577, 2, 1), (1, 300, 3, 1), (2, 240, 2, 1)])
 def test_attention_query_subset(B, N, H, Nq):
     """Only the first Nq tokens of every image are queries (Nq = 1: the CLS-only last layer): forward rows, logsumexp and
     all three gradients equal the full computation with the other queries' upstream gradient set to zero."""

@@ -31,7 +31,8 @@ template <int KVB>
 __global__ void __launch_bounds__(AT_THREADS)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                    const __grid_constant__ CUtensorMap tm_v, __nv_bfloat16* __restrict__ o, long long ldo,
-                   float* __restrict__ lse, int N, int H, float scale) {
+                   float* __restrict__ lse, int N, int Nq, int H, float scale) {
+  // N = keys per item; Nq = queries per item (the first Nq tokens; the grid covers ceil(Nq / AT_QT) query tiles)
   static_assert(KVB % 32 == 0 && KVB <= 256 && KVB / 2 <= AT_O_COL, "key block must be a multiple of 32, <= 256");
   extern __shared__ uint8_t at_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(at_smem_raw) + 1023) & ~uintptr_t(1023));
@@ -203,12 +204,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       for (int i = 0; i < 16; ++i)
         packed[c * 16 + i] = pack_bf16x2(__uint_as_float(r[2 * i]) * inv_l, __uint_as_float(r[2 * i + 1]) * inv_l);
     }
-    if (row < N) {
+    if (row < Nq) {
       const long long tok = static_cast<long long>(b) * N + row;
       uint4* dst = reinterpret_cast<uint4*>(o + tok * ldo + h * AT_HD);
 #pragma unroll
       for (int i = 0; i < 8; ++i) dst[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
-      if (lse != nullptr) lse[(static_cast<long long>(b) * H + h) * N + row] = (m + log2f(l)) * AT_LN2;
+      if (lse != nullptr) lse[(static_cast<long long>(b) * H + h) * Nq + row] = (m + log2f(l)) * AT_LN2;
     }
   }
   tc_fence_before();
@@ -219,10 +220,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
 
 template <int KVB>
 int launch_fwd(const void* q, const void* k, const void* v, long long ld, void* o, long long ldo, float* lse, int B,
-               int N, int H, float scale, cudaStream_t stream) {
+               int N, int Nq, int H, float scale, cudaStream_t stream) {
   CUtensorMap tq, tk, tv;
   const uint64_t D = static_cast<uint64_t>(H) * AT_HD;
-  int rc = encode_tmap_3d_bf16(&tq, q, D, N, B, ld, static_cast<uint64_t>(N) * ld, 64, AT_QT);
+  int rc = encode_tmap_3d_bf16(&tq, q, D, Nq, B, ld, static_cast<uint64_t>(N) * ld, 64, AT_QT);
   if (rc) return rc;
   rc = encode_tmap_3d_bf16(&tk, k, D, N, B, ld, static_cast<uint64_t>(N) * ld, 64, KVB);
   if (rc) return rc;
@@ -235,9 +236,9 @@ int launch_fwd(const void* q, const void* k, const void* v, long long ld, void* 
     if (e != cudaSuccess) return set_error(kErrCuda, "attention_fwd_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  dim3 grid((N + AT_QT - 1) / AT_QT, H, B);
+  dim3 grid((Nq + AT_QT - 1) / AT_QT, H, B);
   kern<<<grid, AT_THREADS, at_smem_bytes<KVB>(), stream>>>(tq, tk, tv, reinterpret_cast<__nv_bfloat16*>(o), ldo, lse, N,
-                                                          H, scale);
+                                                          Nq, H, scale);
   return check_launch("attention_fwd_tc");
 }
 
@@ -259,7 +260,10 @@ __global__ void __launch_bounds__(AT_THREADS)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_r1, const __grid_constant__ CUtensorMap tm_r2,
                    const __grid_constant__ CUtensorMap tm_c1, const __grid_constant__ CUtensorMap tm_c2,
                    const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ out1,
-                   __nv_bfloat16* __restrict__ out2, long long ldout, int N, int H, float scale) {
+                   __nv_bfloat16* __restrict__ out2, long long ldout, int N, int Nq, int H, float scale) {
+  // N = tokens (keys) per item, Nq = queries per item (the first Nq tokens). Rows / columns of this instantiation:
+  constexpr bool kRowsAreKeys = DKV;
+  const int Nr = kRowsAreKeys ? N : Nq, Nc = kRowsAreKeys ? Nq : N;
   extern __shared__ uint8_t at_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(at_smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sR1 = smem;
@@ -278,9 +282,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_r1, const __grid_const
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r0 = blockIdx.x * AT_QT, h = blockIdx.y, b = blockIdx.z;
-  const int nblk = (N + AB_CB - 1) / AB_CB;
-  const float* lrow = lse + (static_cast<long long>(b) * H + h) * N;
-  const float* drow = delta + (static_cast<long long>(b) * H + h) * N;
+  const int nblk = (Nc + AB_CB - 1) / AB_CB;
+  const float* lrow = lse + (static_cast<long long>(b) * H + h) * Nq;    // per query
+  const float* drow = delta + (static_cast<long long>(b) * H + h) * Nq;
 
   if (warp == 4) {
     if (lane == 0) {
@@ -361,21 +365,21 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_r1, const __grid_const
     const int row = r0 + warp * 32 + lane;
     float L_row = INFINITY, D_row = 0.f;
     if constexpr (!DKV) {
-      if (row < N) { L_row = lrow[row] * AT_LOG2E; D_row = drow[row]; }
+      if (row < Nr) { L_row = lrow[row] * AT_LOG2E; D_row = drow[row]; }
     }
     for (int j = 0; j < nblk; ++j) {
       const int buf = j & 1;
       if constexpr (DKV) {
         if (tid < AB_CB) {
           const int i = j * AB_CB + tid;
-          sL[buf * AB_CB + tid] = i < N ? lrow[i] * AT_LOG2E : INFINITY;  // padded query: exp2(-inf) = 0
-          sD[buf * AB_CB + tid] = i < N ? drow[i] : 0.f;
+          sL[buf * AB_CB + tid] = i < Nc ? lrow[i] * AT_LOG2E : INFINITY;  // padded query: exp2(-inf) = 0
+          sD[buf * AB_CB + tid] = i < Nc ? drow[i] : 0.f;
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
       }
       mbar_wait(bar_s, j & 1);
       tc_fence_after();
-      const int nvalid = min(AB_CB, N - j * AB_CB);
+      const int nvalid = min(AB_CB, Nc - j * AB_CB);
 #pragma unroll 1
       for (int c = 0; c < AB_CB / 32; ++c) {
         uint32_t s[32], dp[32];
@@ -431,7 +435,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_r1, const __grid_const
         for (int i = 0; i < 16; ++i)
           packed[c * 16 + i] = pack_bf16x2(__uint_as_float(r[2 * i]) * f, __uint_as_float(r[2 * i + 1]) * f);
       }
-      if (row < N) {
+      if (row < Nr) {
         uint4* dst = reinterpret_cast<uint4*>(dst_base + tok * ldout + h * AT_HD);
 #pragma unroll
         for (int i = 0; i < 8; ++i) dst[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
@@ -447,16 +451,17 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_r1, const __grid_const
 template <bool DKV>
 int launch_bwd(const void* r1, const void* r2, long long ldr1, long long ldr2, const void* c1, const void* c2,
                long long ldc1, long long ldc2, const float* lse, const float* delta, void* out1, void* out2,
-               long long ldout, int B, int N, int H, float scale, cudaStream_t stream) {
+               long long ldout, int B, int N, int Nq, int H, float scale, cudaStream_t stream) {
   CUtensorMap t1, t2, t3, t4;
   const uint64_t D = static_cast<uint64_t>(H) * AT_HD;
-  int rc = encode_tmap_3d_bf16(&t1, r1, D, N, B, ldr1, static_cast<uint64_t>(N) * ldr1, 64, AT_QT);
+  const int Nr = DKV ? N : Nq, Nc = DKV ? Nq : N;  // rows / columns of this half (keys x queries, or queries x keys)
+  int rc = encode_tmap_3d_bf16(&t1, r1, D, Nr, B, ldr1, static_cast<uint64_t>(N) * ldr1, 64, AT_QT);
   if (rc) return rc;
-  rc = encode_tmap_3d_bf16(&t2, r2, D, N, B, ldr2, static_cast<uint64_t>(N) * ldr2, 64, AT_QT);
+  rc = encode_tmap_3d_bf16(&t2, r2, D, Nr, B, ldr2, static_cast<uint64_t>(N) * ldr2, 64, AT_QT);
   if (rc) return rc;
-  rc = encode_tmap_3d_bf16(&t3, c1, D, N, B, ldc1, static_cast<uint64_t>(N) * ldc1, 64, AB_CB);
+  rc = encode_tmap_3d_bf16(&t3, c1, D, Nc, B, ldc1, static_cast<uint64_t>(N) * ldc1, 64, AB_CB);
   if (rc) return rc;
-  rc = encode_tmap_3d_bf16(&t4, c2, D, N, B, ldc2, static_cast<uint64_t>(N) * ldc2, 64, AB_CB);
+  rc = encode_tmap_3d_bf16(&t4, c2, D, Nc, B, ldc2, static_cast<uint64_t>(N) * ldc2, 64, AB_CB);
   if (rc) return rc;
   auto kern = attn_bwd_tc_kernel<DKV>;
   static bool attr_set = false;
@@ -465,9 +470,9 @@ int launch_bwd(const void* r1, const void* r2, long long ldr1, long long ldr2, c
     if (e != cudaSuccess) return set_error(kErrCuda, "attention_bwd_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  dim3 grid((N + AT_QT - 1) / AT_QT, H, B);
+  dim3 grid((Nr + AT_QT - 1) / AT_QT, H, B);
   kern<<<grid, AT_THREADS, AB_SMEM, stream>>>(t1, t2, t3, t4, lse, delta, reinterpret_cast<__nv_bfloat16*>(out1),
-                                             reinterpret_cast<__nv_bfloat16*>(out2), ldout, N, H, scale);
+                                             reinterpret_cast<__nv_bfloat16*>(out2), ldout, N, Nq, H, scale);
   return check_launch(DKV ? "attention_bwd_dkv_tc" : "attention_bwd_dq_tc");
 }
 
@@ -475,11 +480,12 @@ int launch_bwd(const void* r1, const void* r2, long long ldr1, long long ldr2, c
 // delta[b,h,n] = sum_d dO[b,n,h,d] * O[b,n,h,d]; one warp per token, two lanes per head.
 __global__ void __launch_bounds__(256)
 attn_delta_kernel(const __nv_bfloat16* __restrict__ o, long long ldo, const __nv_bfloat16* __restrict__ dout,
-                  long long lddo, float* __restrict__ delta, int B, int N, int H) {
+                  long long lddo, float* __restrict__ delta, int B, int N, int Nq, int H) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long tok = blockIdx.x * 8LL + warp;
-  if (tok >= static_cast<long long>(B) * N) return;
-  const int b = static_cast<int>(tok / N), n = static_cast<int>(tok - static_cast<long long>(b) * N);
+  const long long qtok = blockIdx.x * 8LL + warp;  // index among the B * Nq query tokens
+  if (qtok >= static_cast<long long>(B) * Nq) return;
+  const int b = static_cast<int>(qtok / Nq), n = static_cast<int>(qtok - static_cast<long long>(b) * Nq);
+  const long long tok = static_cast<long long>(b) * N + n;
   for (int hbase = 0; hbase < H; hbase += 16) {  // warp-uniform trip count (full-mask shuffle below)
     const int hh = hbase + (lane >> 1);
     const bool valid = hh < H;
@@ -497,7 +503,7 @@ attn_delta_kernel(const __nv_bfloat16* __restrict__ o, long long ldo, const __nv
       }
     }
     s += __shfl_xor_sync(0xffffffffu, s, 1);
-    if (valid && (lane & 1) == 0) delta[(static_cast<long long>(b) * H + hh) * N + n] = s;
+    if (valid && (lane & 1) == 0) delta[(static_cast<long long>(b) * H + hh) * Nq + n] = s;
   }
 }
 
@@ -505,18 +511,19 @@ attn_delta_kernel(const __nv_bfloat16* __restrict__ o, long long ldo, const __nv
 }  // namespace
 
 int attention_delta(const void* o, long long ldo, const void* dout, long long lddo, float* delta, int B, int N, int H,
-                    cudaStream_t stream) {
-  const long long toks = static_cast<long long>(B) * N;
+                    cudaStream_t stream, int Nq) {
+  if (Nq <= 0) Nq = N;
+  const long long toks = static_cast<long long>(B) * Nq;
   attn_delta_kernel<<<static_cast<int>((toks + 7) / 8), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(o), ldo,
                                                                           reinterpret_cast<const __nv_bfloat16*>(dout),
-                                                                          lddo, delta, B, N, H);
+                                                                          lddo, delta, B, N, Nq, H);
   return check_launch("attention_delta");
 }
 
 int attention_fwd_tc(const void* q, const void* k, const void* v, long long ld, void* o, long long ldo, float* lse,
                      int B, int N, int H, int head_dim, float scale, cudaStream_t stream, int Nq) {
   if (Nq <= 0) Nq = N;
-  if (Nq != N && N > 224) return set_error(kErrUnsupported, "attention: a query subset needs N <= 224 (N=%d)", N);
+  if (Nq > N) return set_error(kErrInvalidArg, "attention: Nq=%d > N=%d", Nq, N);
   if (head_dim != AT_HD) return set_error(kErrUnsupported, "attention: head_dim=%d (only 64 is supported)", head_dim);
   if (B <= 0 || N <= 0) return kOk;
   if ((ld % 8) || (reinterpret_cast<uintptr_t>(q) & 15) || (reinterpret_cast<uintptr_t>(k) & 15) ||
@@ -528,7 +535,7 @@ int attention_fwd_tc(const void* q, const void* k, const void* v, long long ld, 
       return set_error(kErrInvalidArg, "attention: o must be 16-byte aligned with a pitch that is a multiple of 8");
     return attention_fwd_fused(q, k, v, ld, o, ldo, lse, B, N, Nq, H, scale, stream);  // persistent, one key block
   }
-  return launch_fwd<128>(q, k, v, ld, o, ldo, lse, B, N, H, scale, stream);
+  return launch_fwd<128>(q, k, v, ld, o, ldo, lse, B, N, Nq, H, scale, stream);
 }
 
 int attention_bwd_tc(const void* q, const void* k, const void* v, long long ld, const void* o, long long ldo,
@@ -536,7 +543,9 @@ int attention_bwd_tc(const void* q, const void* k, const void* v, long long ld, 
                      long long lddqkv, int B, int N, int H, int head_dim, float scale, cudaStream_t stream,
                      float* bias_grad, int bias_mask, int Nq) {
   if (Nq <= 0) Nq = N;
-  if (Nq != N && N > 256) return set_error(kErrUnsupported, "attention_bwd: a query subset needs N <= 256 (N=%d)", N);
+  if (Nq > N) return set_error(kErrInvalidArg, "attention_bwd: Nq=%d > N=%d", Nq, N);
+  if (N > 256 && Nq != N && Nq != 1 && bias_grad != nullptr && (bias_mask & 1))
+    return set_error(kErrUnsupported, "attention_bwd: the query-bias gradient of a query subset needs Nq = 1 or N <= 256");
   if (head_dim != AT_HD) return set_error(kErrUnsupported, "attention: head_dim=%d (only 64 is supported)", head_dim);
   if (B <= 0 || N <= 0) return kOk;
   if ((ld % 8) || (lddo % 8) || (lddqkv % 8) || (ldo % 8))
@@ -546,16 +555,19 @@ int attention_bwd_tc(const void* q, const void* k, const void* v, long long ld, 
     return attention_bwd_fused(q, k, v, ld, o, ldo, dout, lddo, lse, dq, dk, dv, lddqkv, bias_grad, bias_mask, B, N, Nq, H, scale, stream);
   }
   ProfScope prof("attention_bwd", 10.0 * B * H * static_cast<double>(N) * N * AT_HD, 16.0 * B * H * static_cast<double>(N) * AT_HD, stream);
-  int rc = attention_delta(o, ldo, dout, lddo, delta, B, N, H, stream);
+  int rc = attention_delta(o, ldo, dout, lddo, delta, B, N, H, stream, Nq);
   if (rc) return rc;
   // dQ: rows = queries (Q, dO), columns = keys (K, V)
-  rc = launch_bwd<false>(q, dout, ld, lddo, k, v, ld, ld, lse, delta, dq, nullptr, lddqkv, B, N, H, scale, stream);
+  rc = launch_bwd<false>(q, dout, ld, lddo, k, v, ld, ld, lse, delta, dq, nullptr, lddqkv, B, N, Nq, H, scale, stream);
   if (rc) return rc;
   // dK / dV: rows = keys (K, V), columns = queries (Q, dO)
-  rc = launch_bwd<true>(k, v, ld, ld, q, dout, ld, lddo, lse, delta, dk, dv, lddqkv, B, N, H, scale, stream);
+  rc = launch_bwd<true>(k, v, ld, ld, q, dout, ld, lddo, lse, delta, dk, dv, lddqkv, B, N, Nq, H, scale, stream);
   if (rc || bias_grad == nullptr) return rc;
   const int Dm = H * AT_HD;
-  if (bias_mask & 1) rc = colsum_bf16(dq, lddqkv, B * N, Dm, bias_grad, stream);
+  if (bias_mask & 1) {  // only the query rows of dq exist
+    rc = Nq == N ? colsum_bf16(dq, lddqkv, B * N, Dm, bias_grad, stream)
+                 : colsum_bf16(dq, static_cast<long long>(N) * lddqkv, B, Dm, bias_grad, stream);
+  }
   if (rc) return rc;
   if (bias_mask & 2) rc = colsum_bf16(dk, lddqkv, B * N, Dm, bias_grad + Dm, stream);
   if (rc) return rc;

@@ -140,12 +140,11 @@ int pick_splits(int Mo, int No, int K) {
   return best;
 }
 
-// The last encoder layer is evaluated on the CLS rows only when the sequence fits the fused attention kernels
-// (they take a query subset; the long-sequence kernels do not).
+// The last encoder layer is evaluated on the CLS rows only (every attention kernel takes a query subset).
 bool cls_only_last_layer(const tic_vit_config* c) {
   static const bool full = std::getenv("TIC_FULL_LAST_LAYER") != nullptr;  // development knob: A/B against the full layer
-  const int G = c->image_size / 16;
-  return !full && G * G + 1 <= 224;
+  (void)c;
+  return !full;
 }
 
 #define TIC_TRY(expr)        \
@@ -218,7 +217,7 @@ int vit_forward(const tic_vit_config* c, const float* P32, const void* P16v, con
     // The classifier reads only the CLS row of the last layer's output (modeling_vit.py:641), and inside a layer a
     // token's output depends on the other tokens only through the keys and values. So the last layer projects K and V
     // for every token but runs the query projection, the attention rows, the output projection and the MLP on the
-    // B CLS rows alone (row pitch N*width in the same buffers). Needs the fused attention kernels (query subsets).
+    // B CLS rows alone (row pitch N*width in the same buffers).
     const bool cls_only = cls_only_last_layer(c) && l == c->layers - 1;
     const int rows = cls_only ? B : M;
     const long long rm = cls_only ? N : 1;  // row pitch multiplier of the per-token buffers

@@ -94,7 +94,7 @@ int attention_bwd_fused(const void* q, const void* k, const void* v, long long l
                         const void* dout, long long lddo, const float* lse, void* dq, void* dk, void* dv, long long ldg,
                         float* bias_grad, int bias_mask, int B, int N, int Nq, int H, float scale, cudaStream_t stream);
 int attention_delta(const void* o, long long ldo, const void* dout, long long lddo, float* delta, int B, int N, int H,
-                    cudaStream_t stream);
+                    cudaStream_t stream, int Nq = 0);
 
 // engine.cu
 struct VitLayout {
