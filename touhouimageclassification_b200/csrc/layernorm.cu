@@ -257,7 +257,9 @@ int layernorm_bwd(const void* dy_bf16, long long lddy, const float* x, long long
     return set_error(kErrInvalidArg, "layernorm_bwd: dxsum needs the bf16 dx output");
   static const bool force_static = std::getenv("TIC_LN_STATIC") != nullptr;  // development A/B
   const int dynamic = force_static ? 0 : 1;
-  const int chunk_rows = dynamic ? 8 * LN_WARPS : LN_WARPS;  // dynamic: 8 rows per warp between two hand-outs
+  // dynamic: 8 rows per warp between two hand-outs; a launch too small to fill the machine that way (the B CLS rows of
+  // the final LayerNorm / the CLS-only last layer) gets one row per warp so that the rows still spread over the SMs
+  const int chunk_rows = (dynamic && rows > 8 * LN_WARPS * 2 * 148) ? 8 * LN_WARPS : LN_WARPS;
   int grid = (rows + chunk_rows - 1) / chunk_rows;  // dynamic: one CTA per chunk; running CTAs take over the rest
   const int max_grid = 148 * 2;
   if (!dynamic && grid > max_grid) grid = max_grid;
