@@ -365,7 +365,7 @@ def run_ours(args):
 
     # ---- batched inference (BASELINE config 4: utils/filter + web serve path), per-GPU replica, device-resident inputs
     inference = None
-    if not args.no_inference:
+    if not args.no_inference and world == 1:  # replicas only: N ranks would each repeat the N = 1 measurement
         del trainer
         model._workspaces.clear()            # drop the 46 GB training workspace before the batch-1024 forwards
         torch.cuda.empty_cache()
