@@ -169,6 +169,35 @@ def test_grad_accumulation_semantics():
         assert rel(p.grad, 2 * g1[n]) < 1e-3, n
 
 
+def test_adamw_per_bucket_under_backward_equals_one_update_after_it():
+    """The fused step applies AdamW bucket by bucket on a side stream while the backward of earlier layers runs
+    (parallel.DataParallelTrainer._grad_sync); that must leave the parameters one full-arena update after the backward
+    leaves (AdamW is elementwise: same arithmetic; only the order of the atomically accumulated gradients may differ)."""
+    from touhouimageclassification_b200.finetune import fused_train_step
+    from touhouimageclassification_b200.optim import FusedAdamW
+    from touhouimageclassification_b200.parallel import DataParallelTrainer
+    cfg = dict(hidden_size=128, num_hidden_layers=4, num_attention_heads=2, intermediate_size=256, image_size=32, num_labels=10)
+    x = O.deterministic_images(6, 32, seed=5).to(dev)
+    y = torch.tensor([0, 3, 7, 1, 2, 9], device=dev)
+    arenas, losses = [], []
+    for at_end in (False, True):
+        m = make(cfg, 0.05).train()
+        opt = FusedAdamW(m, lr=1e-3, weight_decay=0.01)
+        sched = DataParallelTrainer(m, opt, local=True, bucket_mb=0.25)   # several buckets even for this small model
+        sched.update_at_end = at_end
+        assert len(sched.buckets) >= 3
+        for _ in range(3):
+            losses.append(float(fused_train_step(m, opt, x, y, grad_sync=sched._grad_sync)))
+        torch.cuda.synchronize()
+        arenas.append(m._arena.clone())
+        assert opt._step == 3 and all(float(st["step"]) == 3.0 for st in opt.state.values())
+    assert losses[:3] == pytest.approx(losses[3:], abs=1e-5)
+    # AdamW's first steps are sign-like (update ~ lr * g / |g|): an element whose gradient is pure accumulation-order
+    # noise may legitimately land 2 * lr apart, so the bound is on how many elements differ, not on the worst one
+    assert ((arenas[0] - arenas[1]).abs() > 1e-5).float().mean().item() < 1e-4
+    assert losses[2] < losses[0]                                          # and it trains
+
+
 def test_serve_and_predict_batch(tmp_path):
     from touhouimageclassification_b200 import serve as S
     m = make(BASE, 0.02)
