@@ -198,7 +198,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from touhouimageclassification_b200 import _lib
-    from touhouimageclassification_b200.finetune import fused_train_step, train_step
+    from touhouimageclassification_b200.finetune import train_step
     from touhouimageclassification_b200.model import ViTConfig, ViTForImageClassification
     from touhouimageclassification_b200.optim import FusedAdamW
     from touhouimageclassification_b200.parallel import DataParallelTrainer

@@ -3,7 +3,6 @@ world_size 2 over gloo (rendezvous on 127.0.0.1)."""
 import os
 import socket
 
-import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp

@@ -21,7 +21,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from ._lib import c_float, c_i64, c_int, c_void_p
+from ._lib import c_i64, c_int, c_void_p
 
 
 # ----------------------------------------------------------------------------------------------------

@@ -6,7 +6,6 @@ memory and streams); no torch operator does arithmetic on this path.
 """
 from __future__ import annotations
 
-import ctypes
 
 import torch
 

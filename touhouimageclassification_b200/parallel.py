@@ -11,7 +11,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from typing import List, Optional, Tuple
+from typing import List, Tuple
 
 import torch
 import torch.distributed as dist

@@ -9,7 +9,7 @@ from __future__ import annotations
 import os
 import queue
 import threading
-from typing import Callable, List, Sequence
+from typing import Callable, List
 
 import torch
 
