@@ -167,3 +167,43 @@ def test_full_judge_csv_and_daemon(tmp_path):
     d.stop()
     flat = [p for i in range(4) for p in res[i]]
     assert [p[0] for p in flat] == [r["predicted_class"] for r in rows]
+
+
+@pytest.mark.gpu
+def test_ntrain_fit_from_uint8_thumbnails_checkpoints_and_reload(tmp_path):
+    """The Lightning-Trainer replacement on the engine (section 8f rank 1): uint8 thumbnails -> fused augmentation ->
+    CutMix/MixUp -> fused step, validation / test through the module's own steps, Lightning-layout checkpoints that
+    load_from_checkpoint and --transform read, resume continuing the step count."""
+    from touhouimageclassification_b200 import ntrain
+    from touhouimageclassification_b200.augment import GpuAugment
+    rng = np.random.default_rng(0)
+    thumbs = torch.from_numpy(rng.integers(0, 256, (8, 64, 64, 3), dtype=np.uint8))
+    labels = torch.tensor([0, 1, 2, 3, 4, 0, 1, 2])
+    train = [(thumbs[:4], labels[:4]), (thumbs[4:], labels[4:])]
+    xv = torch.randn(6, 3, 224, 224, generator=torch.Generator().manual_seed(1))
+    yv = torch.tensor([0, 1, 2, 3, 4, 0])
+    val = [(xv[:4], yv[:4]), (xv[4:], yv[4:])]
+    torch.manual_seed(3)
+    lm = ntrain.ViTLModule(5, False, "google/vit-base-patch16-224", lr=1e-4, weight_decay=0.01, enable_mixup=True,
+                           fused_optimizer=True).cuda()
+    opt = lm.configure_optimizers()
+    st = ntrain.fit(lm, train, val, max_epochs=2, patience=0, checkpoint_dir=str(tmp_path), train_id="g", optimizer=opt,
+                    augment=GpuAugment(seed=5))
+    assert st.epoch == 1 and st.global_step == 4 and opt._step == 4 and len(st.best) == 2
+    assert all(np.isfinite(h[1]) and np.isfinite(h[2]) and 0.0 <= h[3] <= 1.0 for h in st.history)
+    acc = ntrain.test(lm, val)["test_acc"]
+    newest = max(st.best, key=lambda sp: sp[1])[1]
+    again = ntrain.ViTLModule.load_from_checkpoint(newest, num_classes=5, pretrained=False,
+                                                   model_name="google/vit-base-patch16-224", lr=1e-4, weight_decay=0.01).cuda()
+    if newest.endswith(f"epoch=01_val_acc={st.history[1][3]:.4f}.ckpt"):
+        assert ntrain.test(again, val)["test_acc"] == pytest.approx(acc)
+    inner = ntrain.transform_checkpoint(newest, str(tmp_path / "nViT_epoch2.pth"))
+    assert set(inner) == set(lm.vit.state_dict())
+    # resume for one more epoch: epoch, step counters and AdamW moments continue
+    lm2 = ntrain.ViTLModule(5, False, "google/vit-base-patch16-224", lr=1e-4, weight_decay=0.01, enable_mixup=True,
+                            fused_optimizer=True).cuda()
+    opt2 = lm2.configure_optimizers()
+    last = [p for _, p in st.best if "epoch=01" in p][0]
+    st2 = ntrain.fit(lm2, train, val, max_epochs=3, patience=0, checkpoint_dir=str(tmp_path / "r"), train_id="g",
+                     optimizer=opt2, augment=GpuAugment(seed=5), ckpt_path=last)
+    assert [h[0] for h in st2.history] == [2] and st2.global_step == 6 and opt2._step == 6

@@ -124,3 +124,206 @@ class ViTLModule(_Base):
         pred = logits.argmax(dim=1)
         acc = (pred == y).float().mean()
         self.log('test_acc', acc, prog_bar=True)
+
+    if _Base is nn.Module:
+        @classmethod
+        def load_from_checkpoint(cls, checkpoint_path, map_location=None, **ctor):
+            """Lightning's classmethod, as the reference calls it (ntrain.py:190): every constructor argument is passed
+            again because the reference never calls ``save_hyperparameters()``."""
+            ckpt = torch.load(checkpoint_path, map_location=map_location or "cpu", weights_only=False)
+            module = cls(**ctor)
+            module.load_state_dict(ckpt["state_dict"], strict=True)
+            return module
+
+
+# ----------------------------------------------------------------------------------------------------
+# The loop ``L.Trainer(...).fit / .test`` runs for the reference (ntrain.py:219-248) [section 8f rank 1]
+# ----------------------------------------------------------------------------------------------------
+class FitState:
+    """What ``fit`` leaves behind (and what a checkpoint's ``callbacks`` entry restores)."""
+
+    def __init__(self):
+        self.epoch = -1              # last finished epoch (0-based)
+        self.global_step = 0
+        self.best = []               # [(val_acc, path)] of ModelCheckpoint(monitor='val_acc', mode='max', save_top_k)
+        self.periodic = []           # paths of ModelCheckpoint(monitor='epoch', every_n_epochs, save_top_k)
+        self.best_score = None       # EarlyStopping(monitor='val_acc', mode='max')
+        self.wait_count = 0
+        self.stopped_early = False
+        self.history = []            # (epoch, train_loss, val_loss, val_acc)
+
+    def callbacks_state(self):
+        return dict(best=list(self.best), periodic=list(self.periodic), best_score=self.best_score,
+                    wait_count=self.wait_count)
+
+
+def _to_device(batch, device):
+    return tuple(t.to(device, non_blocking=True) if torch.is_tensor(t) else t for t in batch)
+
+
+def _module_device(module):
+    return next(module.parameters()).device
+
+
+def _all_reduce_sums(values):
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        t = torch.tensor(values, dtype=torch.float64, device="cuda" if dist.get_backend() == "nccl" else "cpu")
+        dist.all_reduce(t)
+        return [float(v) for v in t]
+    return values
+
+
+@torch.no_grad()
+def evaluate(lmodule, loader, step: str = "validation_step", device=None):
+    """One pass of ``validation_step`` / ``test_step`` over ``loader``: the logged metrics averaged the way Lightning
+    reduces ``self.log(..., on_epoch=True)`` values -- a mean over batches weighted by batch size."""
+    if not hasattr(lmodule, "logged"):
+        raise TypeError("evaluate() reads the values of self.log(...) from `lmodule.logged` (the Lightning-free ViTLModule); "
+                        "with Lightning installed use its own Trainer")
+    device = device or _module_device(lmodule)
+    was_training = lmodule.training
+    lmodule.eval()
+    sums, count = {}, 0
+    for i, batch in enumerate(loader):
+        batch = _to_device(batch, device)
+        n = len(batch[1])
+        lmodule.logged.clear()
+        getattr(lmodule, step)(batch, i)
+        for k, v in lmodule.logged.items():
+            sums[k] = sums.get(k, 0.0) + float(v) * n
+        count += n
+    lmodule.train(was_training)
+    keys = sorted(sums)
+    red = _all_reduce_sums([sums[k] for k in keys] + [float(count)])
+    total = red[-1]
+    return {k: (red[j] / total if total else 0.0) for j, k in enumerate(keys)}
+
+
+def save_checkpoint(path, lmodule, optimizer, state: FitState):
+    """Lightning's checkpoint layout, reduced to what the reference's tooling reads: ``state_dict`` with ``vit.`` keys
+    (``load_from_checkpoint``, ``--transform``), ``optimizer_states``, ``epoch`` / ``global_step`` for resuming."""
+    import os
+    os.makedirs(os.path.dirname(path) or ".", exist_ok=True)
+    torch.save({"epoch": state.epoch, "global_step": state.global_step, "pytorch-lightning_version": "tic_b200",
+                "state_dict": lmodule.state_dict(), "optimizer_states": [optimizer.state_dict()], "lr_schedulers": [],
+                "callbacks": state.callbacks_state()}, path)
+
+
+def transform_checkpoint(checkpoint_path, out_path):
+    """``ntrain.py --restore CKPT --transform OUT`` (ntrain.py:186-192): the bare inner ``vit`` state_dict (HF keys), the
+    ``nViT_epoch*.pth`` files ``serve.load_model`` reads."""
+    ckpt = torch.load(checkpoint_path, map_location="cpu", weights_only=False)
+    sd = ckpt["state_dict"]
+    inner = {k[len("vit."):]: v for k, v in sd.items() if k.startswith("vit.")}
+    if not inner:
+        raise ValueError(f"{checkpoint_path} holds no 'vit.' parameters")
+    torch.save(inner, out_path)
+    return inner
+
+
+def fit(lmodule, train_loader, val_loader, *, max_epochs: int, patience: int = 3, checkpoint_dir=None,
+        train_id: str = "run", save_top_k: int = 3, every_n_epochs: int = 3, ckpt_path=None, optimizer=None, augment=None,
+        data_parallel=None, device=None, logger=None) -> FitState:
+    """``L.Trainer(max_epochs, callbacks=[ModelCheckpoint(val_acc, max, top 3), ModelCheckpoint(epoch, every 3, top 3),
+    EarlyStopping(val_acc, max, patience)], precision='bf16-mixed').fit(lmodule, datamodule, ckpt_path)``
+    (ntrain.py:219-245) without Lightning.
+
+    Per epoch: every training batch goes through ``fused_training_step`` (engine forward, loss, backward, AdamW; the
+    train transform and CutMix / MixUp run on the device when ``augment`` is given and the loader yields uint8
+    thumbnails) -- or, with a stock optimizer, ``training_step`` + ``backward`` + ``step`` -- then one validation pass,
+    the two checkpoint policies and the early-stopping rule, all on the epoch's ``val_acc``. ``data_parallel`` (a
+    ``DataParallelTrainer`` around ``lmodule.vit``) adds the gradient exchange; metrics are reduced over the ranks and
+    rank 0 writes the files. ``ckpt_path`` resumes (weights, optimizer state, epoch, callback state)."""
+    import logging
+    import os
+    import torch.distributed as dist
+    log = logger or logging.getLogger("tic_b200.ntrain")
+    device = device or _module_device(lmodule)
+    optimizer = optimizer or lmodule.configure_optimizers()
+    rank0 = not (dist.is_available() and dist.is_initialized()) or dist.get_rank() == 0
+    fused = isinstance(optimizer, FusedAdamW)
+    state = FitState()
+    if ckpt_path is not None:
+        ckpt = torch.load(ckpt_path, map_location="cpu", weights_only=False)
+        lmodule.load_state_dict(ckpt["state_dict"], strict=True)
+        if ckpt.get("optimizer_states"):
+            optimizer.load_state_dict(ckpt["optimizer_states"][0])
+        state.epoch = int(ckpt.get("epoch", -1))
+        state.global_step = int(ckpt.get("global_step", 0))
+        cb = ckpt.get("callbacks") or {}
+        state.best = [tuple(b) for b in cb.get("best", [])]
+        state.periodic = list(cb.get("periodic", []))
+        state.best_score = cb.get("best_score")
+        state.wait_count = int(cb.get("wait_count", 0))
+        log.info(f"Restored {ckpt_path}: resuming after epoch {state.epoch}")
+
+    def ckpt_name(epoch, val_acc):
+        return os.path.join(checkpoint_dir, f"checkpoint_{train_id}_epoch={epoch:02d}_val_acc={val_acc:.4f}.ckpt")
+
+    for epoch in range(state.epoch + 1, max_epochs):
+        lmodule.train()
+        running, steps = None, 0
+        for i, batch in enumerate(train_loader):
+            batch = _to_device(batch, device)
+            if fused:
+                kw = {}
+                if data_parallel is not None:
+                    kw = dict(grad_sync=data_parallel._grad_sync, world_size=data_parallel.world_size)
+                loss = lmodule.fused_training_step(batch, optimizer, augment=augment, **kw)
+            else:
+                optimizer.zero_grad()
+                loss = lmodule.training_step(batch, i)
+                loss.backward()
+                optimizer.step()
+            loss = loss.detach().float().reshape(())
+            running = loss if running is None else running + loss   # stays on the device: no sync per step
+            steps += 1
+            state.global_step += 1
+        train_loss = float(running) / steps if steps else 0.0
+        metrics = evaluate(lmodule, val_loader, "validation_step", device) if val_loader is not None else {}
+        val_acc, val_loss = metrics.get("val_acc", 0.0), metrics.get("val_loss", 0.0)
+        state.epoch = epoch
+        state.history.append((epoch, train_loss, val_loss, val_acc))
+        log.info(f"epoch {epoch}: train_loss {train_loss:.4f} val_loss {val_loss:.4f} val_acc {val_acc:.4f}")
+
+        # EarlyStopping(monitor='val_acc', mode='max', patience): counted before the files are written so that a
+        # checkpoint restores the same decision state
+        if state.best_score is None or val_acc > state.best_score:
+            state.best_score, state.wait_count = val_acc, 0
+        else:
+            state.wait_count += 1
+        stop = patience > 0 and state.wait_count >= patience
+
+        if checkpoint_dir is not None and rank0:
+            path = ckpt_name(epoch, val_acc)
+            # ModelCheckpoint(monitor='val_acc', mode='max', save_top_k)
+            keep = len(state.best) < save_top_k or val_acc > min(s for s, _ in state.best)
+            # ModelCheckpoint(monitor='epoch', mode='max', every_n_epochs, save_top_k): the newest periodic files
+            periodic = every_n_epochs > 0 and (epoch + 1) % every_n_epochs == 0
+            if keep:
+                state.best.append((val_acc, path))
+                state.best.sort(key=lambda sp: -sp[0])
+            if periodic:
+                state.periodic.append(path)
+            dropped = []
+            if len(state.best) > save_top_k:
+                dropped.append(state.best.pop()[1])
+            if len(state.periodic) > save_top_k:
+                dropped.append(state.periodic.pop(0))
+            if keep or periodic:
+                save_checkpoint(path, lmodule, optimizer, state)
+            alive = {p for _, p in state.best} | set(state.periodic)
+            for p in dropped:
+                if p not in alive and os.path.exists(p):
+                    os.remove(p)
+        if stop:
+            state.stopped_early = True
+            log.info(f"val_acc has not improved for {patience} epochs: stopping after epoch {epoch}")
+            break
+    return state
+
+
+def test(lmodule, test_loader, device=None):
+    """``trainer.test(lmodule, datamodule)`` (ntrain.py:248): the ``test_acc`` of ``test_step`` over the loader."""
+    return evaluate(lmodule, test_loader, "test_step", device)
