@@ -122,3 +122,44 @@ def test_transform_and_load_from_checkpoint_roundtrip(tmp_path):
     again = ntrain.ViTLModule.load_from_checkpoint(path, num_classes=7, pretrained=False, model_name="google/vit-base-patch16-224",
                                                    lr=1e-5, weight_decay=0.01)
     assert torch.equal(again.vit.classifier.weight, lm.vit.classifier.weight)
+
+
+def _write_folder(root, per_class, size, seed):
+    from PIL import Image
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    for c, n in per_class.items():
+        os.makedirs(os.path.join(root, c), exist_ok=True)
+        for i in range(n):
+            Image.fromarray(rng.integers(0, 256, (size[1], size[0], 3), dtype=np.uint8)).save(os.path.join(root, c, f"{i}.png"))
+
+
+def test_data_module_mirrors_the_reference_surface(tmp_path):
+    """AugmentedDataset (ntrain.py:68-158): ImageFolder class order, 80/20 split, loaders of uint8 thumbnails; the flag
+    chain picks the recipe the reference's setup() composes."""
+    from touhouimageclassification_b200.data import AugmentedDataset, ThumbnailFolder, recipe_from_flags
+    _write_folder(str(tmp_path / "train"), {"reimu": 6, "marisa": 4}, (256, 256), 0)
+    _write_folder(str(tmp_path / "test"), {"reimu": 2, "marisa": 1}, (300, 200), 1)       # odd size: brought to 256 x 256
+    ds = ThumbnailFolder(str(tmp_path / "train"))
+    assert ds.classes == ["marisa", "reimu"] and ds.class_to_idx == {"marisa": 0, "reimu": 1} and len(ds) == 10
+    x, y = ds[0]
+    assert x.dtype == torch.uint8 and x.shape == (256, 256, 3) and y == 0
+    dm = AugmentedDataset(str(tmp_path / "train"), str(tmp_path / "test"), batch_size=4, train_split=0.8, num_workers=0)
+    dm.setup("fit")
+    dm.setup("test")
+    assert len(dm.train_dataset) == 8 and len(dm.val_dataset) == 2 and len(dm.test_dataset) == 3
+    xb, yb = next(iter(dm.train_dataloader()))
+    assert xb.shape == (4, 256, 256, 3) and xb.dtype == torch.uint8 and yb.dtype == torch.int64
+    assert next(iter(dm.test_dataloader()))[0].shape == (3, 256, 256, 3)
+    dm2 = AugmentedDataset(str(tmp_path / "train"), str(tmp_path / "test"), train_split=0.8, num_workers=0)
+    dm2.setup("fit")
+    assert dm2.val_dataset.indices == dm.val_dataset.indices                             # the split is reproducible
+    assert dm.recipe == "full"
+    assert recipe_from_flags(False) == "none" and recipe_from_flags(True, True, True, True) == "grey"
+    assert recipe_from_flags(True, True, False) == "diversity" and recipe_from_flags(True, False, True) == "generalization"
+    with pytest.raises(Exception, match="Must select diversity or generalization"):
+        recipe_from_flags(True, False, False)
+    with pytest.raises(FileNotFoundError):
+        ThumbnailFolder(str(tmp_path / "train" / "reimu"))
+    with pytest.raises(ValueError, match="uint8 batch needs augment"):
+        ntrain.evaluate(Scripted([0.0]), [(xb, yb)])

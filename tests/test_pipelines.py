@@ -192,6 +192,8 @@ def test_ntrain_fit_from_uint8_thumbnails_checkpoints_and_reload(tmp_path):
     assert st.epoch == 1 and st.global_step == 4 and opt._step == 4 and len(st.best) == 2
     assert all(np.isfinite(h[1]) and np.isfinite(h[2]) and 0.0 <= h[3] <= 1.0 for h in st.history)
     acc = ntrain.test(lm, val)["test_acc"]
+    u8 = ntrain.test(lm, [(thumbs, labels)], augment=GpuAugment(seed=0, recipe="none"))["test_acc"]   # uint8 test loader
+    assert 0.0 <= u8 <= 1.0
     newest = max(st.best, key=lambda sp: sp[1])[1]
     again = ntrain.ViTLModule.load_from_checkpoint(newest, num_classes=5, pretrained=False,
                                                    model_name="google/vit-base-patch16-224", lr=1e-4, weight_decay=0.01).cuda()

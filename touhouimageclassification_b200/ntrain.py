@@ -175,9 +175,10 @@ def _all_reduce_sums(values):
 
 
 @torch.no_grad()
-def evaluate(lmodule, loader, step: str = "validation_step", device=None):
+def evaluate(lmodule, loader, step: str = "validation_step", device=None, augment=None):
     """One pass of ``validation_step`` / ``test_step`` over ``loader``: the logged metrics averaged the way Lightning
-    reduces ``self.log(..., on_epoch=True)`` values -- a mean over batches weighted by batch size."""
+    reduces ``self.log(..., on_epoch=True)`` values -- a mean over batches weighted by batch size. uint8 thumbnail
+    batches go through ``augment.tensor`` first (the transform the reference's Dataset applies per sample)."""
     if not hasattr(lmodule, "logged"):
         raise TypeError("evaluate() reads the values of self.log(...) from `lmodule.logged` (the Lightning-free ViTLModule); "
                         "with Lightning installed use its own Trainer")
@@ -188,6 +189,10 @@ def evaluate(lmodule, loader, step: str = "validation_step", device=None):
     for i, batch in enumerate(loader):
         batch = _to_device(batch, device)
         n = len(batch[1])
+        if batch[0].dtype == torch.uint8:
+            if augment is None:
+                raise ValueError("a uint8 batch needs augment=GpuAugment(...) (the reference's Dataset transform)")
+            batch = (augment.tensor(batch[0]),) + tuple(batch[1:])
         lmodule.logged.clear()
         getattr(lmodule, step)(batch, i)
         for k, v in lmodule.logged.items():
@@ -224,7 +229,7 @@ def transform_checkpoint(checkpoint_path, out_path):
 
 def fit(lmodule, train_loader, val_loader, *, max_epochs: int, patience: int = 3, checkpoint_dir=None,
         train_id: str = "run", save_top_k: int = 3, every_n_epochs: int = 3, ckpt_path=None, optimizer=None, augment=None,
-        data_parallel=None, device=None, logger=None) -> FitState:
+        val_augment=None, data_parallel=None, device=None, logger=None) -> FitState:
     """``L.Trainer(max_epochs, callbacks=[ModelCheckpoint(val_acc, max, top 3), ModelCheckpoint(epoch, every 3, top 3),
     EarlyStopping(val_acc, max, patience)], precision='bf16-mixed').fit(lmodule, datamodule, ckpt_path)``
     (ntrain.py:219-245) without Lightning.
@@ -281,7 +286,9 @@ def fit(lmodule, train_loader, val_loader, *, max_epochs: int, patience: int = 3
             steps += 1
             state.global_step += 1
         train_loss = float(running) / steps if steps else 0.0
-        metrics = evaluate(lmodule, val_loader, "validation_step", device) if val_loader is not None else {}
+        metrics = {}
+        if val_loader is not None:  # the reference's validation split carries the training transform (ntrain.py:141-144)
+            metrics = evaluate(lmodule, val_loader, "validation_step", device, val_augment or augment)
         val_acc, val_loss = metrics.get("val_acc", 0.0), metrics.get("val_loss", 0.0)
         state.epoch = epoch
         state.history.append((epoch, train_loss, val_loss, val_acc))
@@ -324,6 +331,6 @@ def fit(lmodule, train_loader, val_loader, *, max_epochs: int, patience: int = 3
     return state
 
 
-def test(lmodule, test_loader, device=None):
+def test(lmodule, test_loader, device=None, augment=None):
     """``trainer.test(lmodule, datamodule)`` (ntrain.py:248): the ``test_acc`` of ``test_step`` over the loader."""
-    return evaluate(lmodule, test_loader, "test_step", device)
+    return evaluate(lmodule, test_loader, "test_step", device, augment)
