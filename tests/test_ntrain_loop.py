@@ -163,3 +163,18 @@ def test_data_module_mirrors_the_reference_surface(tmp_path):
         ThumbnailFolder(str(tmp_path / "train" / "reimu"))
     with pytest.raises(ValueError, match="uint8 batch needs augment"):
         ntrain.evaluate(Scripted([0.0]), [(xb, yb)])
+
+
+def test_train_main_command_line_transform_path(tmp_path):
+    """`ntrain.py --restore CKPT --transform OUT` (ntrain.py:186-192) needs no GPU: it only rewrites the checkpoint."""
+    lm = ntrain.ViTLModule(3, False, "google/vit-base-patch16-224", lr=1e-5, weight_decay=0.01)
+    st = ntrain.FitState()
+    path, out = str(tmp_path / "c.ckpt"), str(tmp_path / "nViT.pth")
+    ntrain.save_checkpoint(path, lm, torch.optim.AdamW(lm.parameters(), lr=1e-5), st)
+    kw = dict(PRETRAINED=False, MODEL_NAME="google/vit-base-patch16-224", LR=1e-5, WEIGHT_DECAY=0.01, FULL_FINETUNE=True,
+              BATCH_SIZE=8, NUM_WORKERS=0, TRAIN_SPLIT=0.8, DATA_DIR="data", MAX_EPOCHS=1, ENABLE_MIX_UP=True,
+              ENABLE_AUGMENTATION=True, TRAIN_ID="t")
+    inner = ntrain.train_main(**kw, argv=["--restore", path, "--transform", out])
+    assert os.path.exists(out) and set(inner) == set(lm.vit.state_dict())
+    with pytest.raises(SystemExit, match="No checkpoint to transform"):
+        ntrain.train_main(**kw, argv=["--transform", out])

@@ -209,3 +209,28 @@ def test_ntrain_fit_from_uint8_thumbnails_checkpoints_and_reload(tmp_path):
     st2 = ntrain.fit(lm2, train, val, max_epochs=3, patience=0, checkpoint_dir=str(tmp_path / "r"), train_id="g",
                      optimizer=opt2, augment=GpuAugment(seed=5), ckpt_path=last)
     assert [h[0] for h in st2.history] == [2] and st2.global_step == 6 and opt2._step == 6
+
+
+@pytest.mark.gpu
+def test_train_main_end_to_end_on_image_folders(tmp_path):
+    """ntrain.train_main (ntrain.py:160-248) from image folders: data module -> fit (device-side transform, CutMix/MixUp,
+    fused steps) -> checkpoints -> test; then --test --restore on the written checkpoint reproduces the test metric."""
+    from PIL import Image
+    from touhouimageclassification_b200 import ntrain
+    rng = np.random.default_rng(0)
+    for split, n in (("train", 5), ("test", 2)):
+        for c in ("a", "b"):
+            os.makedirs(tmp_path / split / c)
+            for i in range(n):
+                Image.fromarray(rng.integers(0, 256, (256, 256, 3), dtype=np.uint8)).save(tmp_path / split / c / f"{i}.png")
+    kw = dict(PRETRAINED=False, MODEL_NAME="google/vit-base-patch16-224", LR=1e-4, WEIGHT_DECAY=0.01, FULL_FINETUNE=True,
+              BATCH_SIZE=4, NUM_WORKERS=0, TRAIN_SPLIT=0.8, DATA_DIR=str(tmp_path / "train"), MAX_EPOCHS=2, ENABLE_MIX_UP=True,
+              ENABLE_AUGMENTATION=True, TRAIN_ID="m", PATIENCE=0, num_classes=2, test_dir=str(tmp_path / "test"),
+              checkpoint_dir=str(tmp_path / "ck"))
+    state, metrics = ntrain.train_main(**kw, argv=[])
+    assert state.epoch == 1 and state.global_step == 4 and 0.0 <= metrics["test_acc"] <= 1.0
+    files = sorted(os.listdir(tmp_path / "ck" / "m"))
+    assert len(files) == 2 and files[0].startswith("checkpoint_m_epoch=00_val_acc=")
+    last = str(tmp_path / "ck" / "m" / files[1])
+    _, again = ntrain.train_main(**kw, argv=["--test", "--restore", last])
+    assert again["test_acc"] == pytest.approx(metrics["test_acc"])

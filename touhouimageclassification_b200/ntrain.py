@@ -334,3 +334,52 @@ def fit(lmodule, train_loader, val_loader, *, max_epochs: int, patience: int = 3
 def test(lmodule, test_loader, device=None, augment=None):
     """``trainer.test(lmodule, datamodule)`` (ntrain.py:248): the ``test_acc`` of ``test_step`` over the loader."""
     return evaluate(lmodule, test_loader, "test_step", device, augment)
+
+
+# the reference's TIC/utils/parameter.py:1-8
+NUM_CLASSES = 120
+VIT_IMAGE_SIZE = 224
+CHECKPOINT_DIR = "checkpoint"
+TEST_DIR = "data/testset"
+
+
+def train_main(PRETRAINED: bool, MODEL_NAME: str, LR: float, WEIGHT_DECAY: float, FULL_FINETUNE: bool, BATCH_SIZE: int,
+               NUM_WORKERS: int, TRAIN_SPLIT: float, DATA_DIR: str, MAX_EPOCHS: int, ENABLE_MIX_UP: bool,
+               ENABLE_AUGMENTATION: bool, TRAIN_ID: str, PATIENCE: int = 3, ONLY_GREY_AUGMENTATION: bool = False,
+               ENABLE_DIVERSITY: bool = True, ENABLE_GENERALIZATION: bool = True, argv=None, num_classes: int = NUM_CLASSES,
+               test_dir: str = TEST_DIR, checkpoint_dir: str = CHECKPOINT_DIR):
+    """``ntrain.train_main`` (ntrain.py:160-248) with the same arguments and command line (``--restore``, ``--test``,
+    ``--transform``): module + data module + the fit / test loop above, on the engine, training from uint8 thumbnails
+    with the transform on the device. Returns what it produced (the bare state_dict for ``--transform``, else the
+    ``FitState`` and the test metrics) instead of exiting."""
+    import argparse
+    import os
+    from .data import AugmentedDataset
+    parser = argparse.ArgumentParser()
+    parser.add_argument("--restore", "-r", type=str, default=None, help="Path to the checkpoint to restore")
+    parser.add_argument("--test", "-t", action="store_true", help="Only test model without training")
+    parser.add_argument("--transform", "-tr", type=str, default=None, help="Transform the checkpoint")
+    args = parser.parse_args(argv)
+    torch.manual_seed(42)  # L.seed_everything(42)
+    if args.transform:
+        if not args.restore:
+            raise SystemExit("No checkpoint to transform")
+        return transform_checkpoint(args.restore, args.transform)
+    lmodel = ViTLModule(num_classes=num_classes, pretrained=PRETRAINED, model_name=MODEL_NAME, lr=LR,
+                        weight_decay=WEIGHT_DECAY, enable_mixup=ENABLE_MIX_UP, full_finetune=FULL_FINETUNE,
+                        fused_optimizer=True).cuda()
+    data = AugmentedDataset(train_path=DATA_DIR, test_path=test_dir, batch_size=BATCH_SIZE, train_split=TRAIN_SPLIT,
+                            num_workers=NUM_WORKERS, image_size=VIT_IMAGE_SIZE, enable_augmentation=ENABLE_AUGMENTATION,
+                            enable_diversity=ENABLE_DIVERSITY, enable_generalization=ENABLE_GENERALIZATION,
+                            only_grey_augmentation=ONLY_GREY_AUGMENTATION)
+    state = None
+    if not args.test:
+        data.setup("fit")
+        state = fit(lmodel, data.train_dataloader(), data.val_dataloader(), max_epochs=MAX_EPOCHS, patience=PATIENCE,
+                    checkpoint_dir=os.path.join(checkpoint_dir, TRAIN_ID), train_id=TRAIN_ID, ckpt_path=args.restore,
+                    augment=data.augment(seed=42))
+    elif args.restore:
+        ckpt = torch.load(args.restore, map_location="cpu", weights_only=False)
+        lmodel.load_state_dict(ckpt["state_dict"], strict=True)
+    data.setup("test")
+    return state, test(lmodel, data.test_dataloader(), augment=data.test_augment())
