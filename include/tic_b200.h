@@ -103,6 +103,10 @@ TIC_API int tic_attention_fwd(const void* q, const void* k, const void* v, int64
 TIC_API int tic_attention_bwd(const void* q, const void* k, const void* v, int64_t ld, const void* o, int64_t ldo,
                               const void* dout, int64_t lddo, const float* lse, float* delta_scratch, void* dq, void* dk,
                               void* dv, int64_t lddqkv, int B, int N, int H, int head_dim, float scale, void* stream);
+/* Number of floats delta_scratch must hold for a backward call of this shape: B*H*N for delta = rowsum(dO o O), plus,
+ * for N > 256, the bf16 dQ partials (one per 128-key tile) that the fused long-sequence kernel writes and a reduction
+ * pass sums. N <= 256 never touches the scratch (one kernel does everything). */
+TIC_API int64_t tic_attention_bwd_scratch_floats(int B, int N, int H);
 
 /* Same backward that also ACCUMULATES the column sums of dq | dk | dv into qkv_bias_grad (fp32 [3 * H * 64]): the bias
  * gradient of the fused QKV Linear (modeling_vit.py:216-230 [a5]). For N <= 256 the whole backward (delta, dQ, dK, dV,
@@ -112,7 +116,7 @@ TIC_API int tic_attention_bwd_bias(const void* q, const void* k, const void* v, 
                                    void* dk, void* dv, int64_t lddqkv, float* qkv_bias_grad, int B, int N, int H,
                                    int head_dim, float scale, void* stream);
 
-/* Query-subset variants (N <= 224 forward, N <= 256 backward): only the first num_queries tokens of every image act as
+/* Query-subset variants: only the first num_queries tokens of every image act as
  * queries -- their rows of o / dout are read, their rows of o / dq written, lse is [B, H, num_queries] -- while all N
  * tokens are keys. The engine uses num_queries = 1 in the LAST encoder layer: only the CLS row of that layer reaches
  * the final LayerNorm and the classifier (modeling_vit.py:455,641-642), so every other row of its attention output,
@@ -135,6 +139,12 @@ TIC_API int tic_head_bwd(const float* dlogits, const void* h_bf16, int64_t ldh, 
                          void* dh_bf16, int64_t lddh, float* dW_accum, float* db_accum, void* stream);
 TIC_API int tic_softmax_xent(const float* logits, const int64_t* hard, const float* soft, int B, int C,
                              float grad_scale, int round_grad_bf16, float* loss, float* dlogits, int32_t* correct,
+                             void* stream);
+
+/* Post-processing of the serving path (TIC/utils/serve.py:107-109, web/runtime.py:117-118: torch.softmax(logits, 1) then
+ * torch.max(probabilities, 1)) in one launch: confidence[b] = max_c softmax(logits[b])[c], index[b] = its class (first
+ * index on ties); probs (optional, may be NULL) receives the whole fp32 distribution [B, C]. */
+TIC_API int tic_softmax_top1(const float* logits, int B, int C, float* confidence, int32_t* index, float* probs,
                              void* stream);
 
 /* ---- fused AdamW --------------------------------------------------------------------------------

@@ -141,7 +141,9 @@ def test_layernorm_eps_is_1e_12_not_fixed():
 
 
 @pytest.mark.parametrize("B,N,H", [(2, 197, 12), (2, 577, 4), (2, 64, 2), (1, 1, 1), (2, 130, 3), (1, 5, 2), (3, 256, 2),
-                                   (2, 128, 1), (2, 129, 2), (2, 192, 2), (2, 193, 1), (2, 65, 2), (1, 257, 2), (64, 197, 16)])
+                                   (2, 128, 1), (2, 129, 2), (2, 192, 2), (2, 193, 1), (2, 65, 2), (1, 257, 2), (64, 197, 16),
+                                   (2, 225, 2), (3, 300, 2), (2, 385, 3), (1, 512, 2), (2, 513, 1), (1, 640, 2), (1, 1000, 1),
+                                   (9, 577, 16)])
 def test_attention_fwd_bwd(B, N, H):
     from touhouimageclassification_b200 import ops
     D = H * 64
@@ -169,6 +171,30 @@ def test_attention_fwd_bwd(B, N, H):
     assert torch.equal(dqkv2, dqkv)
     want = dqkv.float().sum(0) + 0.5
     assert (bg - want).abs().max() <= 1e-4 * max(1.0, want.abs().max().item()) + 1e-5 * B * N
+
+
+@pytest.mark.parametrize("B,N,H", [(2, 577, 2), (1, 300, 1), (2, 197, 2)])
+def test_attention_large_score_range(B, N, H):
+    """Scores spread over hundreds of units with the row maximum moving from key block to key block: exercises the online
+    softmax of the long-sequence forward (lazy rescaling of the running output) and the saved logsumexp in the backward."""
+    from touhouimageclassification_b200 import ops
+    D = H * 64
+    qkv = torch.randn(B * N, 3 * D, device=dev)
+    qkv[:, :D] *= 6.0                                                  # |q.k| / 8 reaches ~ +-150
+    qkv.view(B, N, 3 * D)[:, :, D:2 * D] *= torch.linspace(0.2, 4.0, N, device=dev).view(1, N, 1)  # later keys score higher
+    qkv = qkv.bfloat16()
+    ctx, lse = ops.attention_fwd(qkv, B, N, H)
+    q, k, v = [t.view(B, N, H, 64).transpose(1, 2).float().requires_grad_(True) for t in qkv.float().split(D, dim=1)]
+    s = q @ k.transpose(-1, -2) * 0.125
+    ref = (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(B * N, D)
+    assert torch.isfinite(ctx.float()).all() and rel(ctx, ref) < 5e-3
+    assert (lse - torch.logsumexp(s, -1)).abs().max() < 2e-3 * torch.logsumexp(s, -1).abs().max()
+    dctx = torch.randn(B * N, D, device=dev).bfloat16()
+    ref.backward(dctx.float())
+    dqkv = ops.attention_bwd(qkv, ctx, dctx, lse, B, N, H)
+    assert torch.isfinite(dqkv.float()).all()
+    for ours, t in zip(dqkv.float().split(D, dim=1), (q, k, v)):
+        assert rel(ours, t.grad.transpose(1, 2).reshape(B * N, D)) < 1.5e-2
 
 
 def test_softmax_xent_hard_and_soft():
@@ -220,7 +246,8 @@ def test_patchify_is_exact_and_colsum():
 
 
 @pytest.mark.parametrize("B,N,H,Nq", [(3, 197, 4, 1), (2, 197, 2, 70), (2, 64, 2, 1), (2, 130, 2, 129), (4, 197, 16, 1),
-                                      (2, 577, 2, 1), (1, 300, 3, 1), (2, 240, 2, 1)])
+                                      (2, 577, 2, 1), (1, 300, 3, 1), (2, 240, 2, 1), (2, 577, 2, 130), (1, 640, 1, 300),
+                                      (2, 385, 2, 64), (2, 300, 2, 299)])
 def test_attention_query_subset(B, N, H, Nq):
     """Only the first Nq tokens of every image are queries (Nq = 1: the CLS-only last layer): forward rows, logsumexp and
     all three gradients equal the full computation with the other queries' upstream gradient set to zero."""
@@ -230,8 +257,13 @@ def test_attention_query_subset(B, N, H, Nq):
     ctx_full, lse_full = ops.attention_fwd(qkv, B, N, H)
     ctx, lse = ops.attention_fwd(qkv, B, N, H, num_queries=Nq)
     cf, c = ctx_full.view(B, N, D), ctx.view(B, N, D)
-    assert torch.equal(c[:, :Nq], cf[:, :Nq]) and c[:, Nq:].abs().max() == 0
-    assert torch.equal(lse, lse_full[:, :, :Nq].contiguous())
+    assert c[:, Nq:].abs().max() == 0
+    if N <= 224:   # one key block: a row's arithmetic does not depend on how many rows are queries
+        assert torch.equal(c[:, :Nq], cf[:, :Nq])
+        assert torch.equal(lse, lse_full[:, :, :Nq].contiguous())
+    else:          # long sequences: a tile without a partner splits its key blocks over both softmax groups and merges
+        assert rel(c[:, :Nq], cf[:, :Nq]) < 3e-3
+        assert (lse - lse_full[:, :, :Nq]).abs().max() < 1e-4
     dctx = torch.randn(B * N, D, device=dev).bfloat16()
     dctx.view(B, N, D)[:, Nq:] = 0
     ref = ops.attention_bwd(qkv, ctx_full, dctx, lse_full, B, N, H)

@@ -54,6 +54,10 @@ class GpuAugment:
         return images, ints, floats, ints_d, floats_d
 
     def __call__(self, images: torch.Tensor, first_sample: int = None, return_pixels: bool = False):
+        with torch.cuda.device(images.device):  # the launch goes to the CURRENT device: make it the images' device
+            return self._patchify(images, first_sample, return_pixels)
+
+    def _patchify(self, images, first_sample, return_pixels):
         images, ints, floats, ints_d, floats_d = self._prepare(images, first_sample)
         B, H, W, _ = images.shape
         dev = images.device
@@ -71,6 +75,10 @@ class GpuAugment:
     def tensor(self, images: torch.Tensor, first_sample: int = None) -> torch.Tensor:
         """The batch the reference's DataLoader would hand to ``training_step``: fp32 ``[B, 3, size, size]``, normalised
         (ntrain.py:104-112 ends in ToTensor + Normalize) -- the input of the per-batch CutMix / MixUp (ntrain.py:45-46)."""
+        with torch.cuda.device(images.device):
+            return self._tensor(images, first_sample)
+
+    def _tensor(self, images, first_sample):
         images, ints, floats, ints_d, floats_d = self._prepare(images, first_sample)
         B, H, W, _ = images.shape
         out = torch.empty((B, 3, self.size, self.size), dtype=torch.float32, device=images.device)

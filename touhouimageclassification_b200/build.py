@@ -13,8 +13,12 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB_PATH = os.path.join(CSRC, "libtic_b200.so")
-OBJ_DIR = os.path.join(CSRC, "build")
+# Development variants (kernel experiments compiled with extra -D flags next to the shipped library):
+#   TIC_LIB_VARIANT=name [TIC_VARIANT_FLAGS="-DFOO -DBAR"] python -m touhouimageclassification_b200.build
+# builds csrc/libtic_b200_name.so; a process started with TIC_LIB_VARIANT=name loads that file instead.
+VARIANT = os.environ.get("TIC_LIB_VARIANT", "")
+LIB_PATH = os.path.join(CSRC, f"libtic_b200_{VARIANT}.so" if VARIANT else "libtic_b200.so")
+OBJ_DIR = os.path.join(CSRC, f"build_{VARIANT}" if VARIANT else "build")
 
 NVCC = os.environ.get("TIC_NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = [
@@ -23,7 +27,7 @@ NVCC_FLAGS = [
     "--expt-relaxed-constexpr",
     "-Xcompiler", "-fPIC",
     "-Xcompiler", "-fvisibility=hidden",
-]
+] + (os.environ.get("TIC_VARIANT_FLAGS", "").split() if VARIANT else [])
 
 
 def _sources():

@@ -54,6 +54,8 @@ TIC_API int tic_attention_bwd(const void* q, const void* k, const void* v, int64
                        S(stream));
 }
 
+TIC_API int64_t tic_attention_bwd_scratch_floats(int B, int N, int H) { return attention_bwd_scratch_floats(B, N, H); }
+
 TIC_API int tic_attention_bwd_bias(const void* q, const void* k, const void* v, int64_t ld, const void* o, int64_t ldo,
                                    const void* dout, int64_t lddo, const float* lse, float* delta_scratch, void* dq,
                                    void* dk, void* dv, int64_t lddqkv, float* qkv_bias_grad, int B, int N, int H,
@@ -87,6 +89,10 @@ TIC_API int tic_softmax_xent(const float* logits, const int64_t* hard, const flo
                              void* stream) {
   return softmax_xent(logits, reinterpret_cast<const long long*>(hard), soft, B, C, grad_scale, round_grad_bf16, loss,
                       dlogits, correct, S(stream));
+}
+
+TIC_API int tic_softmax_top1(const float* logits, int B, int C, float* confidence, int32_t* index, float* probs, void* stream) {
+  return softmax_top1(logits, B, C, confidence, index, probs, S(stream));
 }
 
 TIC_API int tic_adamw_step(float* p, const float* g, float* m, float* v, void* shadow_bf16, int64_t n, float lr,

@@ -24,7 +24,6 @@
 // TMEM (512 columns): S[2] 0-127 | dP[2] 128-255 | dV 256-319 | dK 320-383 | dQ[2 query tiles] 384-511.
 #include "tic_internal.cuh"
 
-#include <cstdlib>
 
 namespace tic {
 namespace {
@@ -89,7 +88,11 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
                       int num_items, float scale, long long* __restrict__ trace) {
   // N = keys per item; Nq = queries per item (the first Nq tokens of each image; Nq = 1 for the CLS-only last layer)
   // trace (dev tool, normally NULL): clock64 stamps of CTA 0 -- [0..63] compute warp 0, [64..127] the MMA thread
+#ifdef TIC_ATTN_TRACE  // development build only (-DTIC_ATTN_TRACE): the shipped library has no tracing code
 #define FB_STAMP(slot) do { if (trace != nullptr && blockIdx.x == 0 && it == 3) trace[slot] = clock64(); } while (0)
+#else
+#define FB_STAMP(slot) do { } while (0)
+#endif
   extern __shared__ uint8_t fb_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(fb_smem_raw) + 1023) & ~uintptr_t(1023));
   if (smem + FB_SMEM_USED > fb_smem_raw + FB_SMEM) {  // never observed: the dynamic window starts 1024-byte aligned
@@ -472,32 +475,21 @@ int attention_bwd_fused(const void* q, const void* k, const void* v, long long l
   if (rc) return rc;
   rc = encode_tmap_3d_bf16_sw(&tdv, dv, D, N, B, ldg, static_cast<uint64_t>(N) * ldg, 32, 32, 64);
   if (rc) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM);
-    if (e != cudaSuccess) return set_error(kErrCuda, "attention_bwd_fused: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr_set = true;
-  }
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (num_sms <= 0) num_sms = 148;
-  }
+  if (int rc2 = ensure_dynamic_smem(reinterpret_cast<const void*>(attn_bwd_fused_kernel), FB_SMEM, "attention_bwd_fused")) return rc2;
+  const int num_sms = device_sm_count();
   const int items = B * H;
   if (bias_grad == nullptr) bias_mask = 0;
   dim3 grid(items < num_sms ? items : num_sms);  // persistent: one CTA per SM walks the (image, head) items
   long long* trace = nullptr;
-  static const bool want_trace = getenv("TIC_FB_TRACE") != nullptr;  // dev tool: per-phase clock stamps of CTA 0
-  if (want_trace) {
-    cudaMallocManaged(&trace, 128 * sizeof(long long));
-    for (int i = 0; i < 128; ++i) trace[i] = 0;
-  }
+#ifdef TIC_ATTN_TRACE
+  cudaMallocManaged(&trace, 128 * sizeof(long long));
+  for (int i = 0; i < 128; ++i) trace[i] = 0;
+#endif
   attn_bwd_fused_kernel<<<grid, FB_THREADS, FB_SMEM, stream>>>(
       tq, tk, tv, tdo, to, tdq, tdk, tdv, lse, bias_grad, bias_mask, N, Nq, H, items, scale, trace);
-  if (trace != nullptr) {
-    cudaDeviceSynchronize();
+#ifdef TIC_ATTN_TRACE
+  cudaDeviceSynchronize();
+  {
     const long long t0 = trace[0];
     fprintf(stderr, "[fb trace] compute warp 0 (clk since item start):");
     for (int i = 0; i < 64; ++i) if (trace[i]) fprintf(stderr, " c%d=%lld", i, trace[i] - t0);
@@ -506,6 +498,7 @@ int attention_bwd_fused(const void* q, const void* k, const void* v, long long l
     fprintf(stderr, "\n");
     cudaFree(trace);
   }
+#endif
   return check_launch("attention_bwd_fused");
 }
 

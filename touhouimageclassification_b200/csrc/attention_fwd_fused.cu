@@ -16,7 +16,6 @@
 // direct 16-byte stores at a 2 KB row pitch cost ~300 clk per instruction.
 #include "tic_internal.cuh"
 
-#include <cstdlib>
 
 namespace tic {
 namespace {
@@ -52,7 +51,11 @@ attn_fwd_fused_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
   // N = keys per item; Nq = queries per item (the first Nq tokens of each image: Nq = N normally, Nq = 1 when only the
   // CLS row of the last encoder layer is needed)
   // trace (dev tool, normally NULL): clock64 stamps of CTA 0, third item -- [0..31] warp 0, [32..63] warp 4, [64..] MMA thread
+#ifdef TIC_ATTN_TRACE  // development build only (-DTIC_ATTN_TRACE): the shipped library has no tracing code
 #define FF_STAMP(slot) do { if (trace != nullptr && blockIdx.x == 0 && it == 2) trace[slot] = clock64(); } while (0)
+#else
+#define FF_STAMP(slot) do { } while (0)
+#endif
   extern __shared__ uint8_t ff_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ff_smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sOut = smem + 2 * FF_STAGE_BYTES;
@@ -300,30 +303,19 @@ int attention_fwd_fused(const void* q, const void* k, const void* v, long long l
   if (rc) return rc;
   rc = encode_tmap_3d_bf16(&to, o, D, Nq, B, ldo, static_cast<uint64_t>(N) * ldo, 64, 32);  // one warp's 32-row tile
   if (rc) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_fwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FF_SMEM);
-    if (e != cudaSuccess) return set_error(kErrCuda, "attention_fwd_fused: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr_set = true;
-  }
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (num_sms <= 0) num_sms = 148;
-  }
+  if (int rc2 = ensure_dynamic_smem(reinterpret_cast<const void*>(attn_fwd_fused_kernel), FF_SMEM, "attention_fwd_fused")) return rc2;
+  const int num_sms = device_sm_count();
   const int items = B * H;
   dim3 grid(items < num_sms ? items : num_sms);
   long long* trace = nullptr;
-  static const bool want_trace = getenv("TIC_FF_TRACE") != nullptr;  // dev tool: per-phase clock stamps of CTA 0
-  if (want_trace) {
-    cudaMallocManaged(&trace, 128 * sizeof(long long));
-    for (int i = 0; i < 128; ++i) trace[i] = 0;
-  }
+#ifdef TIC_ATTN_TRACE
+  cudaMallocManaged(&trace, 128 * sizeof(long long));
+  for (int i = 0; i < 128; ++i) trace[i] = 0;
+#endif
   attn_fwd_fused_kernel<<<grid, FF_THREADS, FF_SMEM, stream>>>(tq, tk, tv, to, lse, N, Nq, H, items, scale, trace);
-  if (trace != nullptr) {
-    cudaDeviceSynchronize();
+#ifdef TIC_ATTN_TRACE
+  cudaDeviceSynchronize();
+  {
     const long long t0 = trace[0];
     fprintf(stderr, "[ff trace] tile0 warp:");
     for (int i = 0; i < 32; ++i) if (trace[i]) fprintf(stderr, " a%d=%lld", i, trace[i] - t0);
@@ -334,6 +326,7 @@ int attention_fwd_fused(const void* q, const void* k, const void* v, long long l
     fprintf(stderr, "\n");
     cudaFree(trace);
   }
+#endif
   return check_launch("attention_fwd_fused");
 }
 

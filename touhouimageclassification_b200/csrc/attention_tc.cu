@@ -13,6 +13,8 @@
 // the whole key range is a single block, which is the 197-token case: KVB = 224).
 #include "tic_internal.cuh"
 
+#include <cstdlib>
+
 namespace tic {
 namespace {
 
@@ -230,12 +232,7 @@ int launch_fwd(const void* q, const void* k, const void* v, long long ld, void* 
   rc = encode_tmap_3d_bf16(&tv, v, D, N, B, ld, static_cast<uint64_t>(N) * ld, 64, KVB);
   if (rc) return rc;
   auto kern = attn_fwd_tc_kernel<KVB>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, at_smem_bytes<KVB>());
-    if (e != cudaSuccess) return set_error(kErrCuda, "attention_fwd_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr_set = true;
-  }
+  if (int rc2 = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), at_smem_bytes<KVB>(), "attention_fwd_tc")) return rc2;
   dim3 grid((Nq + AT_QT - 1) / AT_QT, H, B);
   kern<<<grid, AT_THREADS, at_smem_bytes<KVB>(), stream>>>(tq, tk, tv, reinterpret_cast<__nv_bfloat16*>(o), ldo, lse, N,
                                                           Nq, H, scale);
@@ -464,12 +461,7 @@ int launch_bwd(const void* r1, const void* r2, long long ldr1, long long ldr2, c
   rc = encode_tmap_3d_bf16(&t4, c2, D, Nc, B, ldc2, static_cast<uint64_t>(N) * ldc2, 64, AB_CB);
   if (rc) return rc;
   auto kern = attn_bwd_tc_kernel<DKV>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM);
-    if (e != cudaSuccess) return set_error(kErrCuda, "attention_bwd_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr_set = true;
-  }
+  if (int rc2 = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), AB_SMEM, "attention_bwd_tc")) return rc2;
   dim3 grid((Nr + AT_QT - 1) / AT_QT, H, B);
   kern<<<grid, AT_THREADS, AB_SMEM, stream>>>(t1, t2, t3, t4, lse, delta, reinterpret_cast<__nv_bfloat16*>(out1),
                                              reinterpret_cast<__nv_bfloat16*>(out2), ldout, N, Nq, H, scale);
@@ -535,7 +527,11 @@ int attention_fwd_tc(const void* q, const void* k, const void* v, long long ld, 
       return set_error(kErrInvalidArg, "attention: o must be 16-byte aligned with a pitch that is a multiple of 8");
     return attention_fwd_fused(q, k, v, ld, o, ldo, lse, B, N, Nq, H, scale, stream);  // persistent, one key block
   }
-  return launch_fwd<128>(q, k, v, ld, o, ldo, lse, B, N, Nq, H, scale, stream);
+  if ((ldo % 8) || (reinterpret_cast<uintptr_t>(o) & 15))
+    return set_error(kErrInvalidArg, "attention: o must be 16-byte aligned with a pitch that is a multiple of 8");
+  static const bool split_kernels = std::getenv("TIC_ATTN_SPLIT") != nullptr;  // development A/B: the first-generation kernels
+  if (split_kernels) return launch_fwd<128>(q, k, v, ld, o, ldo, lse, B, N, Nq, H, scale, stream);
+  return attention_fwd_long(q, k, v, ld, o, ldo, lse, B, N, Nq, H, scale, stream);  // persistent, K / V ring, online softmax
 }
 
 int attention_bwd_tc(const void* q, const void* k, const void* v, long long ld, const void* o, long long ldo,
@@ -544,8 +540,6 @@ int attention_bwd_tc(const void* q, const void* k, const void* v, long long ld, 
                      float* bias_grad, int bias_mask, int Nq) {
   if (Nq <= 0) Nq = N;
   if (Nq > N) return set_error(kErrInvalidArg, "attention_bwd: Nq=%d > N=%d", Nq, N);
-  if (N > 256 && Nq != N && Nq != 1 && bias_grad != nullptr && (bias_mask & 1))
-    return set_error(kErrUnsupported, "attention_bwd: the query-bias gradient of a query subset needs Nq = 1 or N <= 256");
   if (head_dim != AT_HD) return set_error(kErrUnsupported, "attention: head_dim=%d (only 64 is supported)", head_dim);
   if (B <= 0 || N <= 0) return kOk;
   if ((ld % 8) || (lddo % 8) || (lddqkv % 8) || (ldo % 8))
@@ -554,9 +548,23 @@ int attention_bwd_tc(const void* q, const void* k, const void* v, long long ld, 
     ProfScope prof("attention_bwd", 10.0 * B * H * static_cast<double>(N) * N * AT_HD, 16.0 * B * H * static_cast<double>(N) * AT_HD, stream);
     return attention_bwd_fused(q, k, v, ld, o, ldo, dout, lddo, lse, dq, dk, dv, lddqkv, bias_grad, bias_mask, B, N, Nq, H, scale, stream);
   }
-  ProfScope prof("attention_bwd", 10.0 * B * H * static_cast<double>(N) * N * AT_HD, 16.0 * B * H * static_cast<double>(N) * AT_HD, stream);
-  int rc = attention_delta(o, ldo, dout, lddo, delta, B, N, H, stream, Nq);
+  int rc;
+  {
+    ProfScope prof("attention_delta", 0.0, 4.0 * B * static_cast<double>(Nq) * H * AT_HD, stream);
+    rc = attention_delta(o, ldo, dout, lddo, delta, B, N, H, stream, Nq);
+  }
   if (rc) return rc;
+  static const bool split_kernels = std::getenv("TIC_ATTN_SPLIT") != nullptr;  // development A/B: the first-generation kernels
+  if (!split_kernels && N <= attention_bwd_long_max_queries()) {
+    // one fused kernel; dQ is accumulated over the key tiles in per-CTA fp32 slabs that sit behind delta in the scratch
+    // buffer (attention_bwd_scratch_floats)
+    const long long delta_floats = (static_cast<long long>(B) * H * N + 63) / 64 * 64;
+    ProfScope prof("attention_bwd", 10.0 * B * H * static_cast<double>(N) * N * AT_HD,
+                   2.0 * B * H * AT_HD * (4.0 * N + 3.0 * Nq), stream);
+    return attention_bwd_long(q, k, v, ld, dout, lddo, lse, delta, delta + delta_floats, dq, dk, dv, lddqkv, bias_grad, bias_mask,
+                              B, N, Nq, H, scale, stream);
+  }
+  ProfScope prof("attention_bwd", 10.0 * B * H * static_cast<double>(N) * N * AT_HD, 16.0 * B * H * static_cast<double>(N) * AT_HD, stream);
   // dQ: rows = queries (Q, dO), columns = keys (K, V)
   rc = launch_bwd<false>(q, dout, ld, lddo, k, v, ld, ld, lse, delta, dq, nullptr, lddqkv, B, N, Nq, H, scale, stream);
   if (rc) return rc;

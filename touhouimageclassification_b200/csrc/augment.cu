@@ -353,13 +353,10 @@ int augment_patchify(const void* images_u8, int B, int H, int W, const int* ints
   if (H > 3 * size || W > 3 * size)
     return set_error(kErrUnsupported, "augment_patchify: source %dx%d is more than 3x the output size", H, W);
   const int smem = static_cast<int>((sizeof(AugTables) + 15) / 16 * 16) + 3 * size * size;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(augment_patchify_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>((sizeof(AugTables) + 15) / 16 * 16) + 3 * AUG_MAX_SIZE * AUG_MAX_SIZE);
-    if (e != cudaSuccess) return set_error(kErrCuda, "augment_patchify: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr_set = true;
-  }
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(augment_patchify_kernel),
+                                   static_cast<int>((sizeof(AugTables) + 15) / 16 * 16) + 3 * AUG_MAX_SIZE * AUG_MAX_SIZE,
+                                   "augment_patchify"))
+    return rc;
   ProfScope prof("augment_patchify", 0.0, static_cast<double>(B) * (static_cast<double>(H) * W * 3 + (size / 16) * (size / 16) * 768.0 * 2), stream);
   augment_patchify_kernel<<<B, AUG_THREADS, smem, stream>>>(
       reinterpret_cast<const unsigned char*>(images_u8), H, W, ints_dev, floats_dev, size, mean3_host[0], mean3_host[1],

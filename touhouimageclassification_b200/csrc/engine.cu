@@ -113,7 +113,7 @@ Workspace carve(const tic_vit_config* c, int B, bool training) {
     w.dh = take(M * D * 2);
     w.dqkv = take(M * 3 * D * 2);
     w.dctx = take(M * D * 2);
-    w.delta = take(static_cast<long long>(B) * H * N * 4);
+    w.delta = take(attention_bwd_scratch_floats(B, static_cast<int>(N), static_cast<int>(H)) * 4);  // delta (+ dQ partials, N > 256)
     w.dhcls = take(static_cast<long long>(B) * D * 2);
     w.dpatch = take(static_cast<long long>(B) * P * D * 2);
   } else {

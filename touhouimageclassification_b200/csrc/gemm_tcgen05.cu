@@ -495,33 +495,16 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   }
 }
 
-int g_num_sms = 0;
-
-int num_sms() {
-  if (g_num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_num_sms <= 0) g_num_sms = 148;
-  }
-  return g_num_sms;
-}
-
 constexpr int kNcta = 2;  // CTA pairs (tcgen05 cta_group::2)
 
 template <bool A_MN, bool B_MN, int EPI>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
   using C = Cfg<kNcta, epi_warps<EPI>()>;
   auto kern = gemm_bf16_tcgen05_kernel<A_MN, B_MN, EPI, kNcta>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
-    if (e != cudaSuccess) return set_error(kErrCuda, "gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr_set = true;
-  }
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), C::SMEM_BYTES, "gemm")) return rc;
   const int m_blocks = (p.M + C::TILE_M - 1) / C::TILE_M, n_blocks = (p.N + BN - 1) / BN;
   const int total = m_blocks * n_blocks * p.splits;
-  const int max_workers = num_sms() / kNcta;
+  const int max_workers = device_sm_count() / kNcta;
   // dynamic: one cluster per tile, the running ones take over the rest (see the kernel); TIC_GEMM_STATIC=1 keeps the
   // fixed persistent grid (development A/B)
   static const bool force_static = std::getenv("TIC_GEMM_STATIC") != nullptr;

@@ -259,9 +259,9 @@ int layernorm_bwd(const void* dy_bf16, long long lddy, const float* x, long long
   const int dynamic = force_static ? 0 : 1;
   // dynamic: 8 rows per warp between two hand-outs; a launch too small to fill the machine that way (the B CLS rows of
   // the final LayerNorm / the CLS-only last layer) gets one row per warp so that the rows still spread over the SMs
-  const int chunk_rows = (dynamic && rows > 8 * LN_WARPS * 2 * 148) ? 8 * LN_WARPS : LN_WARPS;
+  const int chunk_rows = (dynamic && rows > 8 * LN_WARPS * 2 * device_sm_count()) ? 8 * LN_WARPS : LN_WARPS;
   int grid = (rows + chunk_rows - 1) / chunk_rows;  // dynamic: one CTA per chunk; running CTAs take over the rest
-  const int max_grid = 148 * 2;
+  const int max_grid = device_sm_count() * 2;
   if (!dynamic && grid > max_grid) grid = max_grid;
   ProfScope prof("layernorm_bwd", 0.0, static_cast<double>(rows) * D * (2 + 4 + (dres ? 4 : 0) + 4 + (dx_bf16 ? 2 : 0)), stream);
   auto* dyb = reinterpret_cast<const __nv_bfloat16*>(dy_bf16);
@@ -269,10 +269,8 @@ int layernorm_bwd(const void* dy_bf16, long long lddy, const float* x, long long
 #define TIC_LN_BWD(V)                                                                                             \
   case V: {                                                                                                       \
     const int smem = 3 * LN_WARPS * V * 32 * 16;                                                                  \
-    static bool attr_set = false;                                                                                 \
-    if (!attr_set && smem > 48 * 1024) {                                                                          \
-      cudaFuncSetAttribute(ln_bwd_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);                  \
-      attr_set = true;                                                                                            \
+    if (smem > 48 * 1024) {                                                                                       \
+      if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(ln_bwd_kernel<V>), smem, "layernorm_bwd")) return rc; \
     }                                                                                                             \
     ln_bwd_kernel<V><<<grid, LN_WARPS * 32, smem, stream>>>(dyb, lddy, x, ldx, mean, rstd, gamma, dres, lddres, rows, \
                                                             dx, lddx, dxb, lddxb, dgamma, dbeta, dxsum, dynamic, \

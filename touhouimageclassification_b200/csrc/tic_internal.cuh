@@ -10,6 +10,11 @@ const char* last_error();
 long long launch_count();
 void prof_enable(bool on);
 long long prof_collect(char* buf, long long buflen);
+// Per-device launch state (runtime.cu): several devices may be driven from one process.
+int current_device();
+int device_sm_count();                                                     // SM count of the current device (cached)
+int ensure_dynamic_smem(const void* func, int bytes, const char* what);   // once per (device, kernel)
+void tmap_cache_stats(long long* hits, long long* misses);
 // RAII: when profiling is enabled, brackets one kernel launch with CUDA events on its stream.
 struct ProfScope {
   ProfScope(const char* name, double flops, double bytes, cudaStream_t s);
@@ -63,6 +68,8 @@ int head_bwd(const float* dlogits, const void* h_bf16, long long ldh, const void
 int softmax_xent(const float* logits, const long long* hard, const float* soft, int B, int C, float grad_scale,
                  int round_grad, float* loss, float* dlogits, int* correct, cudaStream_t stream);
 
+int softmax_top1(const float* logits, int B, int C, float* conf, int* idx, float* probs, cudaStream_t stream);
+
 // adamw.cu
 int adamw_step(float* p, const float* g, float* m, float* v, void* shadow_bf16, long long n, float lr, float beta1,
                float beta2, float eps, float weight_decay, int step, float grad_scale, cudaStream_t stream);
@@ -89,6 +96,16 @@ int attention_bwd_tc(const void* q, const void* k, const void* v, long long ld, 
 // attention_fwd_fused.cu (N <= 224: persistent kernel, both query tiles of a head per CTA, operands prefetched)
 int attention_fwd_fused(const void* q, const void* k, const void* v, long long ld, void* o, long long ldo, float* lse, int B,
                         int N, int Nq, int H, float scale, cudaStream_t stream);
+// attention_fwd_long.cu (N > 224: persistent, two query tiles per CTA ping-pong over a K / V ring, online softmax)
+int attention_fwd_long(const void* q, const void* k, const void* v, long long ld, void* o, long long ldo, float* lse, int B,
+                       int N, int Nq, int H, float scale, cudaStream_t stream);
+// attention_bwd_long.cu (256 < N <= 640): one fused kernel, CTAs own (image, head) pairs and walk their 128-key tiles;
+// dK / dV complete per tile, dQ accumulated over the tiles in a private fp32 slab per CTA (dq_scratch, L2-resident).
+long long attention_bwd_scratch_floats(int B, int N, int H);
+int attention_bwd_long_max_queries();
+int attention_bwd_long(const void* q, const void* k, const void* v, long long ld, const void* dout, long long lddo,
+                       const float* lse, const float* delta, float* dq_scratch, void* dq, void* dk, void* dv, long long ldg,
+                       float* bias_grad, int bias_mask, int B, int N, int Nq, int H, float scale, cudaStream_t stream);
 // attention_bwd_fused.cu
 int attention_bwd_fused(const void* q, const void* k, const void* v, long long ld, const void* o, long long ldo,
                         const void* dout, long long lddo, const float* lse, void* dq, void* dk, void* dv, long long ldg,

@@ -142,7 +142,44 @@ xent_kernel(const float* __restrict__ logits, const long long* __restrict__ hard
   }
 }
 
+// serve.serve / ModelDaemon.predict post-processing (serve.py:107-109, web/runtime.py:117-118): softmax over the class
+// logits, then the maximum probability and its index. One warp per row; probability of the arg-max = 1 / sum exp(l - max).
+__global__ void __launch_bounds__(256)
+softmax_top1_kernel(const float* __restrict__ logits, int B, int C, float* __restrict__ conf, int* __restrict__ idx,
+                    float* __restrict__ probs) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * 8 + warp;
+  if (b >= B) return;
+  const float* lr = logits + static_cast<long long>(b) * C;
+  float mx = -INFINITY;
+  int amax = 0;
+  for (int c = lane; c < C; c += 32) {
+    const float v = lr[c];
+    if (v > mx) { mx = v; amax = c; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float om = __shfl_xor_sync(0xffffffffu, mx, o);
+    const int oa = __shfl_xor_sync(0xffffffffu, amax, o);
+    if (om > mx || (om == mx && oa < amax)) { mx = om; amax = oa; }
+  }
+  float se = 0.f;
+  for (int c = lane; c < C; c += 32) se += expf(lr[c] - mx);
+  se = warp_sum(se);
+  const float inv = 1.0f / se;
+  if (probs != nullptr)
+    for (int c = lane; c < C; c += 32) probs[static_cast<long long>(b) * C + c] = expf(lr[c] - mx) * inv;
+  if (lane == 0) { conf[b] = inv; idx[b] = amax; }
+}
+
 }  // namespace
+
+int softmax_top1(const float* logits, int B, int C, float* conf, int* idx, float* probs, cudaStream_t stream) {
+  if (B <= 0) return kOk;
+  if (conf == nullptr || idx == nullptr) return set_error(kErrInvalidArg, "softmax_top1: conf / idx outputs are required");
+  softmax_top1_kernel<<<(B + 7) / 8, 256, 0, stream>>>(logits, B, C, conf, idx, probs);
+  return check_launch("softmax_top1");
+}
 
 int head_fwd(const void* h_bf16, long long ldh, const void* w_bf16, const float* bias, int B, int D, int C,
              int round_out, float* logits, cudaStream_t stream) {

@@ -161,6 +161,22 @@ def param_layout(cfg: ViTConfig):
     return int(total), list(offs), list(nums), int(head)
 
 
+def _on_model_device(fn):
+    """Run an engine call with the model's device current. Kernel launches, tensor-map encodes and the stream handed to
+    the C-ABI belong to the CURRENT device; a replica on ``cuda:1``, or a worker thread (whose current device defaults
+    to 0), would otherwise launch on the wrong GPU with this model's pointers."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(self, *args, **kwargs):
+        dev = self._arena.device
+        if dev.type != "cuda" or dev.index == torch.cuda.current_device():
+            return fn(self, *args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(self, *args, **kwargs)
+    return wrapper
+
+
 class ViTForImageClassification(nn.Module):
     """B200-native stand-in for ``transformers.ViTForImageClassification`` (modeling_vit.py:605-653)."""
 
@@ -195,8 +211,11 @@ class ViTForImageClassification(nn.Module):
         self.precision = "bf16"
         self._w6 = None
         self._w6_key = None
-        # CUDA graphs of the inference forward for small batches (the web / serve path is launch-bound at batch 1-64)
+        # CUDA graphs of the inference forward for small batches (the web / serve path is launch-bound at batch 1-64).
+        # Batches are padded up to the next bucket, so at most len(graph_buckets) graphs + workspaces are ever retained
+        # (a dynamic batcher produces every size from 1 to 64).
         self.graph_max_batch = 64
+        self.graph_buckets = (1, 2, 4, 8, 16, 32, 64)
         self._graphs = {}
 
     # ---- structure ------------------------------------------------------------------------------
@@ -300,6 +319,7 @@ class ViTForImageClassification(nn.Module):
     def _version_key(self):
         return sum(p._version for p in self._params_in_order())
 
+    @_on_model_device
     def refresh_shadow(self, force: bool = False):
         """Bring the bf16 shadow up to date with the fp32 parameters (one cast kernel over the arena)."""
         if not self._arena_ok():
@@ -310,7 +330,7 @@ class ViTForImageClassification(nn.Module):
             force = True
         if force or key != self._shadow_key:
             _lib.check(_lib.load().tic_cast_f32_to_bf16(c_void_p(self._arena.data_ptr()), c_void_p(self._shadow.data_ptr()),
-                                                        c_i64(self._total), _stream()))
+                                                        c_i64(self._total), _stream(self._arena.device)))
             self._shadow_key = key
 
     def set_precision(self, precision: str):
@@ -323,6 +343,7 @@ class ViTForImageClassification(nn.Module):
             self._w6_key = None
         return self
 
+    @_on_model_device
     def _refresh_w6(self):
         """Split weights for the fp32 mode: every GEMM weight as three bf16 terms laid out [N, 6K]."""
         if not self._arena_ok():
@@ -339,9 +360,10 @@ class ViTForImageClassification(nn.Module):
             self._w6_key = None
         if key != self._w6_key:
             _lib.check(lib.tic_vit_prepare_w6(ctypes.byref(c), c_void_p(self._arena.data_ptr()),
-                                              c_void_p(self._w6.data_ptr()), _stream()))
+                                              c_void_p(self._w6.data_ptr()), _stream(self._arena.device)))
             self._w6_key = key
 
+    @_on_model_device
     def engine_forward_f32(self, pixel_values: torch.Tensor) -> torch.Tensor:
         """fp32-mode forward (tic_vit_forward_f32): fp32 NCHW pixels -> fp32 logits."""
         with self._lock:
@@ -367,7 +389,7 @@ class ViTForImageClassification(nn.Module):
             logits = torch.empty((batch, self.config.num_labels), dtype=torch.float32, device=self._arena.device)
             _lib.check(lib.tic_vit_forward_f32(
                 ctypes.byref(c), c_void_p(self._arena.data_ptr()), c_void_p(self._w6.data_ptr()), c_void_p(x.data_ptr()),
-                c_int(batch), c_void_p(ws.data_ptr()), c_i64(ws.numel()), c_void_p(logits.data_ptr()), _stream()))
+                c_int(batch), c_void_p(ws.data_ptr()), c_i64(ws.numel()), c_void_p(logits.data_ptr()), _stream(self._arena.device)))
             return logits
 
     def mark_shadow_fresh(self):
@@ -415,6 +437,7 @@ class ViTForImageClassification(nn.Module):
             raise RuntimeError("the B200 ViT runs on CUDA only: move the model and pixel_values to the GPU "
                                "(there is no CPU fallback)")
 
+    @_on_model_device
     def engine_forward(self, pixel_values=None, patches=None, training=False) -> torch.Tensor:
         """Raw engine forward: fp32 NCHW pixels or bf16 patch rows -> fp32 logits [B, num_labels]."""
         with self._lock:
@@ -441,7 +464,7 @@ class ViTForImageClassification(nn.Module):
                 ctypes.byref(c), c_void_p(self._arena.data_ptr()), c_void_p(self._shadow.data_ptr()),
                 c_void_p(0 if x is None else x.data_ptr()), c_void_p(0 if patches is None else patches.data_ptr()),
                 c_int(batch), c_void_p(ws.data_ptr()), c_i64(ws.numel()), c_int(int(training)),
-                c_void_p(logits.data_ptr()), _stream()))
+                c_void_p(logits.data_ptr()), _stream(self._arena.device)))
             return logits
 
     def _graph_forward(self, x: torch.Tensor, batch: int) -> torch.Tensor:
@@ -449,33 +472,36 @@ class ViTForImageClassification(nn.Module):
         encodes) of a ViT-L forward cost more host time than device time below batch 64. The graph is captured once per
         batch size over static input / logits / workspace buffers; weights are read through the (stable) shadow arena,
         which refresh_shadow() keeps current outside the graph."""
-        entry = self._graphs.get(batch)
+        bucket = next((b for b in self.graph_buckets if b >= batch), batch)
+        entry = self._graphs.get(bucket)
         if entry is None or entry["shadow_ptr"] != self._shadow.data_ptr() or entry["arena_ptr"] != self._arena.data_ptr():
             dev = self._arena.device
-            ws = self._workspace(batch, False)
-            xin = torch.empty_like(x)
-            out = torch.empty((batch, self.config.num_labels), dtype=torch.float32, device=dev)
+            ws = self._workspace(bucket, False)
+            xin = torch.zeros((bucket,) + tuple(x.shape[1:]), dtype=x.dtype, device=dev)
+            out = torch.empty((bucket, self.config.num_labels), dtype=torch.float32, device=dev)
             c = self.config.to_c()
 
             def launch():
                 _lib.check(_lib.load().tic_vit_forward(
                     ctypes.byref(c), c_void_p(self._arena.data_ptr()), c_void_p(self._shadow.data_ptr()),
-                    c_void_p(xin.data_ptr()), c_void_p(0), c_int(batch), c_void_p(ws.data_ptr()), c_i64(ws.numel()),
-                    c_int(0), c_void_p(out.data_ptr()), _stream()))
+                    c_void_p(xin.data_ptr()), c_void_p(0), c_int(bucket), c_void_p(ws.data_ptr()), c_i64(ws.numel()),
+                    c_int(0), c_void_p(out.data_ptr()), _stream(dev)))
 
-            xin.copy_(x)
             launch()  # eager warm-up: one-time function attributes and driver entry points are set outside the capture
-            torch.cuda.current_stream().synchronize()
+            torch.cuda.current_stream(dev).synchronize()
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            # thread_local: another thread of the process (a DataLoader pin-memory thread, a second replica) may call
+            # cudaHostAlloc / cudaMalloc while this one captures; the default 'global' mode would fail the capture
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
                 launch()
             entry = dict(graph=graph, x=xin, out=out, ws=ws, shadow_ptr=self._shadow.data_ptr(),
                          arena_ptr=self._arena.data_ptr())
-            self._graphs[batch] = entry
-        entry["x"].copy_(x)
+            self._graphs[bucket] = entry
+        entry["x"][:batch].copy_(x)
         entry["graph"].replay()
-        return entry["out"].clone()
+        return entry["out"][:batch].clone()
 
+    @_on_model_device
     def engine_backward(self, dlogits: torch.Tensor, batch: int, head_only: bool = False, stage_begin: int = 0,
                         stage_end: Optional[int] = None):
         """Accumulate parameter gradients of the last training forward into ``grad_arena()``."""
@@ -493,7 +519,7 @@ class ViTForImageClassification(nn.Module):
             _lib.check(_lib.load().tic_vit_backward(
                 ctypes.byref(c), c_void_p(self._arena.data_ptr()), c_void_p(self._shadow.data_ptr()), c_int(batch),
                 c_void_p(ws.data_ptr()), c_i64(ws.numel()), c_void_p(dl.data_ptr()), c_void_p(g.data_ptr()),
-                c_int(stage_begin), c_int(stage_end), c_int(int(head_only)), _stream()))
+                c_int(stage_begin), c_int(stage_end), c_int(int(head_only)), _stream(self._arena.device)))
 
     # ---- nn.Module surface ------------------------------------------------------------------------
     def forward(self, pixel_values=None, labels=None, interpolate_pos_encoding=None, **kwargs):
@@ -518,12 +544,13 @@ class ViTForImageClassification(nn.Module):
             logits = logits.to(torch.get_autocast_dtype("cuda"))
         loss = None
         if labels is not None:
-            loss = torch.nn.functional.cross_entropy(logits.float().view(-1, self.num_labels), labels.view(-1))
+            from . import ops
+            loss = ops.cross_entropy(logits.view(-1, self.num_labels), labels.view(-1))
         return ImageClassifierOutput(logits=logits, loss=loss)
 
 
-def _stream():
-    return c_void_p(torch.cuda.current_stream().cuda_stream)
+def _stream(device=None):
+    return c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
 class _ViTFunction(torch.autograd.Function):

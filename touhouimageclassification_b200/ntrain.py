@@ -83,7 +83,7 @@ class ViTLModule(_Base):
         if self.enable_mixup:
             x, y, _ = cutmix_or_mixup(x, y, self.num_classes)
         logits = self.vit(x).logits
-        loss = F.cross_entropy(logits.float(), y)
+        loss = ops.cross_entropy(logits, y)  # F.cross_entropy (ntrain.py:48) on the fused softmax-CE kernel
         self.log('train_loss', loss, prog_bar=True)
         return loss
 
@@ -112,17 +112,16 @@ class ViTLModule(_Base):
     def validation_step(self, batch, batch_idx):
         x, y = batch
         logits = self.vit(x).logits
-        loss = F.cross_entropy(logits.float(), y)
-        self.log('val_loss', loss, prog_bar=True)
-        pred = logits.argmax(dim=1)
-        acc = (pred == y).float().mean()
+        loss, _, correct = ops.softmax_xent(logits, y, need_grad=False)  # loss + arg-max hits in one launch
+        self.log('val_loss', loss.view(()), prog_bar=True)
+        acc = (correct.float() / y.shape[0]).view(())
         self.log('val_acc', acc, prog_bar=True)
 
     def test_step(self, batch, batch_idx):
         x, y = batch
         logits = self.vit(x).logits
-        pred = logits.argmax(dim=1)
-        acc = (pred == y).float().mean()
+        _, _, correct = ops.softmax_xent(logits, y, need_grad=False)
+        acc = (correct.float() / y.shape[0]).view(())
         self.log('test_acc', acc, prog_bar=True)
 
     if _Base is nn.Module:

@@ -7,6 +7,8 @@ memory and streams); no torch operator does arithmetic on this path.
 from __future__ import annotations
 
 
+import ctypes
+
 import torch
 
 from . import _lib
@@ -23,12 +25,31 @@ def _s():
     return c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def _guarded(fn):
+    """Run ``fn`` with the device of its first CUDA tensor argument current: kernels, tensor maps and the stream handed to
+    the C-ABI all belong to the CURRENT device, which need not be the tensors' device (a replica on cuda:1, a worker
+    thread whose current device defaults to 0)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        for a in list(args) + list(kwargs.values()):
+            if isinstance(a, torch.Tensor) and a.is_cuda:
+                if a.device.index == torch.cuda.current_device():
+                    break
+                with torch.cuda.device(a.device):
+                    return fn(*args, **kwargs)
+        return fn(*args, **kwargs)
+    return wrapper
+
+
 def _require_cuda(*ts):
     for t in ts:
         if t is not None and not t.is_cuda:
             raise ValueError("tic_b200 ops take CUDA tensors only (no CPU fallback)")
 
 
+@_guarded
 def gemm_bf16(a, b, *, a_mn_major=False, b_mn_major=False, epilogue=EPI_BF16, bias=None, aux=None, aux_int=0,
               out=None, out2=None, splits=1):
     """``D = A @ B^T`` on tcgen05. ``a``: [M,K] (or [K,M] when ``a_mn_major``); ``b``: [N,K] (or [K,N])."""
@@ -60,6 +81,7 @@ def gemm_bf16(a, b, *, a_mn_major=False, b_mn_major=False, epilogue=EPI_BF16, bi
     return out
 
 
+@_guarded
 def layernorm_fwd(x, gamma, beta, eps, out_bf16=True, out_f32=False):
     _require_cuda(x, gamma, beta)
     rows, D = x.shape
@@ -72,6 +94,7 @@ def layernorm_fwd(x, gamma, beta, eps, out_bf16=True, out_f32=False):
     return y, yf, mean, rstd
 
 
+@_guarded
 def layernorm_bwd(dy, x, mean, rstd, gamma, dres=None):
     _require_cuda(dy, x, mean, rstd, gamma, dres)
     rows, D = x.shape
@@ -87,6 +110,7 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, dres=None):
     return dx, dxb, dgamma, dbeta, dxsum
 
 
+@_guarded
 def attention_fwd(qkv, B, N, H, scale=0.125, need_lse=True, num_queries=None):
     """qkv: bf16 [B*N, 3*H*64] (q | k | v column blocks). Returns ctx bf16 [B*N, H*64], lse fp32 [B,H,N].
     ``num_queries`` = Nq: only the first Nq tokens of every image are queries (other ctx rows are left zero, lse [B,H,Nq])."""
@@ -108,6 +132,15 @@ def attention_fwd(qkv, B, N, H, scale=0.125, need_lse=True, num_queries=None):
     return ctx, lse
 
 
+def _attention_bwd_scratch(B, N, H, device):
+    """delta (+ the bf16 dQ partials of the fused long-sequence kernel for N > 256): tic_attention_bwd_scratch_floats."""
+    lib = _lib.load()
+    lib.tic_attention_bwd_scratch_floats.restype = ctypes.c_int64
+    n = lib.tic_attention_bwd_scratch_floats(c_int(B), c_int(N), c_int(H))
+    return torch.empty(int(n), device=device, dtype=torch.float32)
+
+
+@_guarded
 def attention_bwd(qkv, ctx, dctx, lse, B, N, H, scale=0.125, bias_grad=None, num_queries=None):
     """dqkv [B*N, 3D] bf16. ``bias_grad`` (fp32 [3D], optional) accumulates the column sums of dqkv (QKV bias gradient).
     ``num_queries`` = Nq: only the first Nq tokens of every image are queries (dq of the other rows is left zero)."""
@@ -115,7 +148,7 @@ def attention_bwd(qkv, ctx, dctx, lse, B, N, H, scale=0.125, bias_grad=None, num
     D = H * 64
     dqkv = torch.empty_like(qkv) if num_queries is None else torch.zeros_like(qkv)
     if num_queries is not None:
-        delta = torch.empty((B, H, N), device=qkv.device, dtype=torch.float32)
+        delta = _attention_bwd_scratch(B, N, H, qkv.device)
         base, dbase = qkv.data_ptr(), dqkv.data_ptr()
         _lib.check(_lib.load().tic_attention_bwd_nq(c_void_p(base), c_void_p(base + 2 * D), c_void_p(base + 4 * D),
                                                     c_i64(3 * D), _p(ctx), c_i64(D), _p(dctx), c_i64(D), _p(lse), _p(delta),
@@ -123,7 +156,7 @@ def attention_bwd(qkv, ctx, dctx, lse, B, N, H, scale=0.125, bias_grad=None, num
                                                     c_i64(3 * D), _p(bias_grad), c_int(B), c_int(N), c_int(num_queries),
                                                     c_int(H), c_int(64), c_float(scale), _s()))
         return dqkv
-    delta = torch.empty((B, H, N), device=qkv.device, dtype=torch.float32)
+    delta = _attention_bwd_scratch(B, N, H, qkv.device)
     base, dbase = qkv.data_ptr(), dqkv.data_ptr()
     if bias_grad is None:
         _lib.check(_lib.load().tic_attention_bwd(c_void_p(base), c_void_p(base + 2 * D), c_void_p(base + 4 * D), c_i64(3 * D),
@@ -140,6 +173,7 @@ def attention_bwd(qkv, ctx, dctx, lse, B, N, H, scale=0.125, bias_grad=None, num
     return dqkv
 
 
+@_guarded
 def softmax_xent(logits, target, grad_scale=None, round_grad=False, need_grad=True):
     """target: int64 [B] (hard) or float [B,C] (soft). Returns (loss[1], dlogits|None, correct[1] int32)."""
     _require_cuda(logits, target)
@@ -157,6 +191,44 @@ def softmax_xent(logits, target, grad_scale=None, round_grad=False, need_grad=Tr
     return loss, dl, correct
 
 
+class _SoftmaxXent(torch.autograd.Function):
+    """``F.cross_entropy`` (mean reduction, integer or soft targets) as one ``tic_softmax_xent`` launch: the forward also
+    produces d loss / d logits, which the backward hands to autograd scaled by the upstream gradient."""
+
+    @staticmethod
+    def forward(ctx, logits, target):
+        loss, dl, _ = softmax_xent(logits.detach(), target, need_grad=True)
+        ctx.save_for_backward(dl)
+        ctx.in_dtype = logits.dtype
+        return loss.view(())
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (dl,) = ctx.saved_tensors
+        return (dl * grad_out).to(ctx.in_dtype), None
+
+
+def cross_entropy(logits, target):
+    """Drop-in for ``F.cross_entropy(logits, target)`` as the reference calls it (finetune.py:61 integer labels,
+    ntrain.py:48 soft MixUp / CutMix targets) on the engine's fused softmax-CE kernel, differentiable w.r.t. ``logits``."""
+    return _SoftmaxXent.apply(logits, target)
+
+
+@_guarded
+def softmax_top1(logits, want_probs=False):
+    """``torch.softmax(logits, 1)`` + ``torch.max(probabilities, 1)`` of the serving path in one launch.
+    Returns (confidence fp32 [B], index int32 [B], probabilities fp32 [B, C] | None)."""
+    _require_cuda(logits)
+    B, C = logits.shape
+    lg = logits if (logits.dtype == torch.float32 and logits.is_contiguous()) else logits.float().contiguous()
+    conf = torch.empty(B, device=lg.device, dtype=torch.float32)
+    idx = torch.empty(B, device=lg.device, dtype=torch.int32)
+    probs = torch.empty((B, C), device=lg.device, dtype=torch.float32) if want_probs else None
+    _lib.check(_lib.load().tic_softmax_top1(_p(lg), c_int(B), c_int(C), _p(conf), _p(idx), _p(probs), _s()))
+    return conf, idx, probs
+
+
+@_guarded
 def adamw_step(p, g, m, v, shadow, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):
     _require_cuda(p, g, m, v, shadow)
     _lib.check(_lib.load().tic_adamw_step(_p(p), _p(g), _p(m), _p(v), _p(shadow), c_i64(p.numel()), c_float(lr),
@@ -164,6 +236,7 @@ def adamw_step(p, g, m, v, shadow, lr, beta1, beta2, eps, weight_decay, step, gr
                                           c_int(step), c_float(grad_scale), _s()))
 
 
+@_guarded
 def patchify_f32(x):
     _require_cuda(x)
     B, C, S, _ = x.shape
@@ -172,6 +245,7 @@ def patchify_f32(x):
     return out
 
 
+@_guarded
 def mix_batch(x, y, num_classes, mode, lam, box, lam_label, want_pixels=True, want_patches=False):
     """CutMix (mode 2) / MixUp (mode 1) of a device batch against its roll(1, 0), fused with the patchify.
     Returns (mixed fp32 pixels | None, soft labels fp32 [B, C], bf16 patch rows | None)."""
@@ -193,6 +267,7 @@ def mix_batch(x, y, num_classes, mode, lam, box, lam_label, want_pixels=True, wa
     return mixed, soft, patches
 
 
+@_guarded
 def colsum_bf16(dy):
     _require_cuda(dy)
     rows, cols = dy.shape

@@ -13,6 +13,7 @@ from typing import Callable, List
 
 import torch
 
+from . import ops
 from .model import ViT, ViTForImageClassification
 
 
@@ -58,20 +59,50 @@ def load_model(model_type: str, num_classes: int, weights_path: str = None, devi
 
 
 def serve(model, image_tensor, class_to_idx, device: str = 'cuda'):
-    """serve.serve (serve.py:83-114): one preprocessed image (batch dimension added) -> (class name, confidence)."""
+    """serve.serve (serve.py:83-114): one preprocessed image (batch dimension added) -> (class name, confidence).
+
+    Precision: the reference runs this forward in plain fp32 (no autocast, serve.py:99-101). Here the arithmetic is the
+    model's ``precision``: ``'bf16'`` (tensor-core engine, the default of ``load_model``) or ``'fp32'`` (logits within 1e-4
+    of the reference's; ``load_model(..., precision='fp32')``). softmax + max run in one kernel (``tic_softmax_top1``)."""
     model.eval()
     idx_to_class = {v: k for k, v in class_to_idx.items()}
     with torch.no_grad():
         image_tensor = image_tensor.to(device)
         output = model(image_tensor)
         logits = output.logits if hasattr(output, 'logits') else output
-        probabilities = torch.softmax(logits.float(), dim=1)
-        confidence, predicted_idx = torch.max(probabilities, 1)
-        predicted_class = idx_to_class[predicted_idx.item()]
-    return predicted_class, confidence.item()
+        confidence, predicted_idx, _ = ops.softmax_top1(logits)
+        pair = torch.stack([confidence, predicted_idx.to(confidence.dtype)]).cpu().tolist()  # one device->host copy
+        predicted_class = idx_to_class[int(pair[1][0])]
+    return predicted_class, pair[0][0]
 
 
-_predict_lock = threading.Lock()
+def _model_lock(model):
+    """Serialises the forwards of ONE model (its workspaces and graphs are per model); replicas on other GPUs have their
+    own lock and run concurrently."""
+    lock = getattr(model, "_lock", None)
+    if lock is None:
+        lock = model._lock = threading.RLock()
+    return lock
+
+
+def _forward_logits(model, pixels=None, patches=None):
+    """Engine forward of a preprocessed batch in the model's precision (``set_precision``): bf16 tensor-core engine, or the
+    fp32-accurate engine, which takes pixels only."""
+    if getattr(model, "precision", "bf16") == "fp32":
+        if pixels is None:
+            raise RuntimeError("precision='fp32' serves from preprocessed fp32 pixels; the uint8 -> bf16 patch pipeline "
+                               "(preprocess_u8) rounds its output to bf16 -- use preprocess_u8_pixels or precision='bf16'")
+        return model.engine_forward_f32(pixels)
+    if patches is not None:
+        return model.engine_forward(patches=patches)
+    return model.engine_forward(pixels, training=False)
+
+
+def _top1_to_host(logits, idx_to_class, results):
+    conf, idx, _ = ops.softmax_top1(logits)
+    for c, k in torch.stack([conf, idx.to(conf.dtype)], 1).cpu().tolist():  # one device->host copy per chunk
+        k = int(k)
+        results.append((idx_to_class[k] if idx_to_class is not None else k, c))
 
 
 def preprocess_u8(images_u8: torch.Tensor, mean, std, size: int = 224) -> torch.Tensor:
@@ -81,7 +112,18 @@ def preprocess_u8(images_u8: torch.Tensor, mean, std, size: int = 224) -> torch.
     from .augment import GpuAugment
     mean = [float(m) for m in mean]
     std = [float(s) for s in std]
-    return GpuAugment(seed=0, size=size, recipe="none", mean=mean, std=std)(images_u8, first_sample=0)
+    with torch.cuda.device(images_u8.device):
+        return GpuAugment(seed=0, size=size, recipe="none", mean=mean, std=std)(images_u8, first_sample=0)
+
+
+def preprocess_u8_pixels(images_u8: torch.Tensor, mean, std, size: int = 224) -> torch.Tensor:
+    """Same transform, yielding what the reference's transform yields: the normalised fp32 tensor [B, 3, size, size]
+    (input of the fp32-accurate engine)."""
+    from .augment import GpuAugment
+    mean = [float(m) for m in mean]
+    std = [float(s) for s in std]
+    with torch.cuda.device(images_u8.device):
+        return GpuAugment(seed=0, size=size, recipe="none", mean=mean, std=std).tensor(images_u8, first_sample=0)
 
 
 def predict_batch_u8(model: ViTForImageClassification, images_u8: torch.Tensor, mean, std, idx_to_class=None,
@@ -90,15 +132,16 @@ def predict_batch_u8(model: ViTForImageClassification, images_u8: torch.Tensor, 
     out -- resize + normalise + patchify in one kernel, bf16 engine forward, softmax/max, one host copy per chunk."""
     model.eval()
     results = []
-    with torch.no_grad(), _predict_lock:
+    dev = model._arena.device
+    fp32 = getattr(model, "precision", "bf16") == "fp32"
+    with torch.no_grad(), _model_lock(model):
         for i in range(0, images_u8.shape[0], max_batch_size):
-            chunk = images_u8[i:i + max_batch_size].to(model._arena.device, non_blocking=True)
-            logits = model.engine_forward(patches=preprocess_u8(chunk, mean, std, model.config.image_size))
-            prob = torch.softmax(logits, dim=1)
-            conf, idx = torch.max(prob, 1)
-            for c, k in torch.stack([conf, idx.to(conf.dtype)], 1).cpu().tolist():
-                k = int(k)
-                results.append((idx_to_class[k] if idx_to_class is not None else k, c))
+            chunk = images_u8[i:i + max_batch_size].to(dev, non_blocking=True)
+            if fp32:
+                logits = _forward_logits(model, pixels=preprocess_u8_pixels(chunk, mean, std, model.config.image_size))
+            else:
+                logits = _forward_logits(model, patches=preprocess_u8(chunk, mean, std, model.config.image_size))
+            _top1_to_host(logits, idx_to_class, results)
     return results
 
 
@@ -106,20 +149,80 @@ def predict_batch(model: ViTForImageClassification, image_batch: torch.Tensor, i
                   max_batch_size: int = 1024):
     """Forward part of ``ModelDaemon.predict`` / ``serve_batch`` (runtime.py:113-124, 243-246): a stacked batch of
     preprocessed images -> list of (class, confidence). Chunks by ``max_batch_size`` and is safe to call from
-    several threads (the Flask app calls predict outside its lock, runtime.py:237-246)."""
+    several threads (the Flask app calls predict outside its lock, runtime.py:237-246). Runs in the model's precision
+    (``load_model(..., precision=...)``): the reference's is fp32, the default here is the bf16 tensor-core engine."""
     model.eval()
     results = []
-    with torch.no_grad(), _predict_lock:
+    dev = model._arena.device
+    with torch.no_grad(), _model_lock(model):
         for i in range(0, image_batch.shape[0], max_batch_size):
-            chunk = image_batch[i:i + max_batch_size].to(model._arena.device, non_blocking=True)
-            logits = model.engine_forward(chunk, training=False)
-            prob = torch.softmax(logits, dim=1)
-            conf, idx = torch.max(prob, 1)
-            both = torch.stack([conf, idx.to(conf.dtype)], 1).cpu()
-            for c, k in both.tolist():
-                k = int(k)
-                results.append((idx_to_class[k] if idx_to_class is not None else k, c))
+            chunk = image_batch[i:i + max_batch_size].to(dev, non_blocking=True)
+            _top1_to_host(_forward_logits(model, pixels=chunk), idx_to_class, results)
     return results
+
+
+class ReplicaPool:
+    """Per-GPU inference replicas (BASELINE config 4 / SURVEY 8e: "one module per GPU, requests round-robined, no
+    collective"). One copy of the model per device, one worker thread per replica; ``predict_u8`` / ``predict`` split a
+    request into per-replica chunks, run them concurrently and return the results in request order."""
+
+    def __init__(self, model: ViTForImageClassification, devices=None):
+        import copy
+        if devices is None:
+            devices = [f"cuda:{i}" for i in range(torch.cuda.device_count())]
+        if not devices:
+            raise RuntimeError("ReplicaPool needs at least one CUDA device (there is no CPU path)")
+        self.devices = [torch.device(d) for d in devices]
+        self.replicas = []
+        for d in self.devices:
+            if model._arena.device == d:
+                rep = model
+            else:
+                rep = copy.deepcopy(model).to(d)
+                rep._lock = threading.RLock()
+                rep.set_precision(model.precision)
+            self.replicas.append(rep.eval())
+        from concurrent.futures import ThreadPoolExecutor
+        self._pool = ThreadPoolExecutor(max_workers=len(self.replicas), thread_name_prefix="tic-replica")
+        self._next = 0
+
+    def __len__(self):
+        return len(self.replicas)
+
+    def _split(self, n: int, chunk: int):
+        """Contiguous chunks of at most ``chunk`` items, dealt round-robin to the replicas (continuing from the last call)."""
+        plan = []
+        for start in range(0, n, chunk):
+            plan.append((self._next % len(self.replicas), start, min(n, start + chunk)))
+            self._next += 1
+        return plan
+
+    def _run(self, fn, n: int, chunk: int):
+        if chunk is None:
+            chunk = max(1, -(-n // len(self.replicas)))
+        plan = self._split(n, chunk)
+        futures = [self._pool.submit(fn, self.replicas[r], a, b) for r, a, b in plan]
+        out = []
+        for f in futures:
+            out.extend(f.result())
+        return out
+
+    def predict_u8(self, images_u8: torch.Tensor, mean, std, idx_to_class=None, chunk: int = None):
+        """uint8 NHWC thumbnails (host, ideally pinned) -> list of (class, confidence), all replicas working at once."""
+        def work(rep, a, b):
+            with torch.cuda.device(rep._arena.device):
+                return predict_batch_u8(rep, images_u8[a:b], mean, std, idx_to_class, max_batch_size=b - a)
+        return self._run(work, images_u8.shape[0], chunk)
+
+    def predict(self, image_batch: torch.Tensor, idx_to_class=None, chunk: int = None):
+        """Preprocessed fp32 NCHW batch -> list of (class, confidence)."""
+        def work(rep, a, b):
+            with torch.cuda.device(rep._arena.device):
+                return predict_batch(rep, image_batch[a:b], idx_to_class, max_batch_size=b - a)
+        return self._run(work, image_batch.shape[0], chunk)
+
+    def close(self):
+        self._pool.shutdown(wait=True)
 
 
 # ----------------------------------------------------------------------------------------------------------------------
