@@ -5,7 +5,9 @@ device-time share per kernel and, when the DRAM counters are present, bytes per 
     python scripts/ncu_launch_summary.py gpurun_out/launches.csv [--json out.json]
 """
 import csv
+import hashlib
 import io
+import os
 import json
 import re
 import sys
@@ -17,6 +19,17 @@ def to_base(value: str, unit: str) -> float:
     scale = {"ns": 1e-3, "us": 1.0, "usecond": 1.0, "ms": 1e3, "msecond": 1e3, "second": 1e6, "nsecond": 1e-3,
              "byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     return v * scale.get(unit, 1.0)
+
+
+def gemm_sources_sha():
+    """Hash of the sources the GEMM kernel is compiled from: bench.py only quotes the DRAM traffic of a capture whose
+    hash equals the tree's (a changed kernel nulls the number instead of silently keeping a stale one)."""
+    csrc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "touhouimageclassification_b200", "csrc")
+    h = hashlib.sha256()
+    for f in ("gemm_tcgen05.cu", "tic_common.cuh", "tic_internal.cuh"):
+        with open(os.path.join(csrc, f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
 
 
 def main():
@@ -52,6 +65,7 @@ def main():
                            dram_bytes_per_launch=gemm["bytes"] / gemm["n"])
         print(f"\nall GEMM launches: {100 * gemm['us'] / total_us:.1f}% of the device time, "
               f"{gemm['bytes'] / gemm['n'] / 1e6:.1f} MB of DRAM traffic per launch")
+    out["gemm_sources_sha"] = gemm_sources_sha()
     if "--json" in sys.argv:
         json.dump(out, open(sys.argv[sys.argv.index("--json") + 1], "w"), indent=1)
 

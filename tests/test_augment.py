@@ -161,6 +161,12 @@ def test_augmented_patches_feed_the_engine():
     assert GpuAugment(seed=3).__call__(imgs, first_sample=0).equal(patches)       # deterministic in (seed, index)
     with pytest.raises(ValueError):
         GpuAugment()(imgs.cpu())
+    # data-parallel shards: rank r's local batch is the slice [r*B, (r+1)*B) of the global batch, step after step
+    whole = GpuAugment(seed=3)
+    r0, r1 = GpuAugment(seed=3).shard(0, 2), GpuAugment(seed=3).shard(1, 2)
+    for _ in range(2):
+        g = whole(imgs)
+        assert torch.equal(torch.cat([r0(imgs[:2]), r1(imgs[2:])]), g)
 
 
 @pytest.mark.gpu

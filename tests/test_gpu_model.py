@@ -317,7 +317,7 @@ def test_small_batch_inference_graph_matches_eager_and_tracks_weight_updates():
         m.graph_max_batch = 64
         g1 = m(x).logits.clone()
         g2 = m(x).logits.clone()
-        assert torch.equal(g1, eager) and torch.equal(g2, eager) and 4 in m._graphs   # batch 3 runs in the bucket of 4
+        assert torch.equal(g1, eager) and torch.equal(g2, eager) and (4, False) in m._graphs   # batch 3 runs in the bucket of 4
         x5 = O.deterministic_images(5, 32, seed=2).to(dev)
         m.graph_max_batch = 0
         e5 = m(x5).logits.clone()
@@ -325,7 +325,10 @@ def test_small_batch_inference_graph_matches_eager_and_tracks_weight_updates():
         assert torch.equal(m(x5).logits, e5) and torch.equal(m(x).logits, eager)
         for bs in range(1, 17):                            # a dynamic batcher produces every size: graphs stay bounded
             m(O.deterministic_images(bs, 32, seed=3).to(dev))
-        assert set(m._graphs) <= set(m.graph_buckets) and len(m._graphs) <= 5
+        assert {k[0] for k in m._graphs} <= set(m.graph_buckets) and len(m._graphs) <= 5
+        from touhouimageclassification_b200 import ops
+        pt = ops.patchify_f32(x)                           # bf16 patch rows (the uint8 serving pipeline's input) replay a graph too
+        assert torch.equal(m.engine_forward(patches=pt), eager) and (4, True) in m._graphs
         m.classifier.bias.add_(0.25)                       # in-place weight update: the shadow is refreshed outside the graph
         assert torch.allclose(m(x).logits, eager + 0.25, atol=2e-2)
         m.to("cpu"); m.to(dev)                             # new arena -> the graph is rebuilt

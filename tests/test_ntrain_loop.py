@@ -65,7 +65,10 @@ def test_checkpoint_policies_and_early_stopping(tmp_path):
                                             "checkpoint_t_epoch=04_val_acc=0.6500.ckpt", "checkpoint_t_epoch=05_val_acc=0.6400.ckpt"]
     ck = torch.load(st.best[0][1], weights_only=False)
     assert ck["epoch"] == 3 and ck["global_step"] == 12 and set(ck["state_dict"]) == {"lin.weight", "lin.bias"}
-    assert len(ck["optimizer_states"]) == 1 and ck["callbacks"]["best_score"] == pytest.approx(0.70)
+    assert len(ck["optimizer_states"]) == 1 and ck["tic_callbacks"]["best_score"] == pytest.approx(0.70)
+    # what Lightning's own loader (migrate_checkpoint) needs from the file: a parseable version and callbacks keyed by state_key
+    from packaging.version import Version
+    assert Version(ck["pytorch-lightning_version"]) >= Version("2.0.0") and ck["callbacks"] == {} and ck["lr_schedulers"] == []
 
 
 def test_patience_zero_disables_early_stopping_and_no_dir_writes_nothing(tmp_path):

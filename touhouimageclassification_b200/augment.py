@@ -38,6 +38,14 @@ class GpuAugment:
         self._mean = (ctypes.c_float * 3)(*[float(np.float32(m)) for m in mean])
         self._std = (ctypes.c_float * 3)(*[float(np.float32(s)) for s in std])
         self.samples_seen = 0
+        self.rank, self.world_size = 0, 1
+
+    def shard(self, rank: int, world_size: int):
+        """Data-parallel use: every rank's batch of B is the slice [rank * B, (rank + 1) * B) of a global batch of
+        world_size * B, so the augmentation parameters stay a function of (seed, GLOBAL sample index) and no two ranks
+        draw the same ones."""
+        self.rank, self.world_size = int(rank), int(world_size)
+        return self
 
     def _prepare(self, images: torch.Tensor, first_sample):
         if not images.is_cuda or images.dtype != torch.uint8 or images.dim() != 4 or images.shape[-1] != 3:
@@ -45,8 +53,8 @@ class GpuAugment:
         images = images.contiguous()
         B, H, W, _ = images.shape
         if first_sample is None:
-            first_sample = self.samples_seen
-            self.samples_seen += B
+            first_sample = self.samples_seen + self.rank * B
+            self.samples_seen += B * self.world_size
         ints, floats = sample_params(self.seed, first_sample, B, H, W, self.size, self.recipe)
         dev = images.device
         ints_d = torch.from_numpy(ints).to(dev, non_blocking=True)

@@ -453,8 +453,8 @@ class ViTForImageClassification(nn.Module):
                 assert patches.dtype == torch.bfloat16 and patches.is_cuda and patches.is_contiguous()
                 batch = patches.shape[0] // P
                 x = None
-            if not training and x is not None and batch <= self.graph_max_batch and not torch.cuda.is_current_stream_capturing():
-                return self._graph_forward(x, batch)
+            if not training and batch <= self.graph_max_batch and not torch.cuda.is_current_stream_capturing():
+                return self._graph_forward(x if x is not None else patches, batch, from_patches=x is None)
             ws = self._workspace(batch, training)
             if training:
                 self._ws_generation += 1
@@ -467,24 +467,27 @@ class ViTForImageClassification(nn.Module):
                 c_void_p(logits.data_ptr()), _stream(self._arena.device)))
             return logits
 
-    def _graph_forward(self, x: torch.Tensor, batch: int) -> torch.Tensor:
+    def _graph_forward(self, x: torch.Tensor, batch: int, from_patches: bool = False) -> torch.Tensor:
         """Inference forward of a small batch as ONE CUDA-graph launch: the ~220 kernel launches (and their tensor-map
         encodes) of a ViT-L forward cost more host time than device time below batch 64. The graph is captured once per
         batch size over static input / logits / workspace buffers; weights are read through the (stable) shadow arena,
         which refresh_shadow() keeps current outside the graph."""
         bucket = next((b for b in self.graph_buckets if b >= batch), batch)
-        entry = self._graphs.get(bucket)
+        key = (bucket, from_patches)
+        entry = self._graphs.get(key)
         if entry is None or entry["shadow_ptr"] != self._shadow.data_ptr() or entry["arena_ptr"] != self._arena.data_ptr():
             dev = self._arena.device
             ws = self._workspace(bucket, False)
-            xin = torch.zeros((bucket,) + tuple(x.shape[1:]), dtype=x.dtype, device=dev)
+            rows = x.shape[0] // batch if from_patches else 1  # patch rows per image (bf16 [B * P, 768] input)
+            xin = torch.zeros((bucket * rows,) + tuple(x.shape[1:]), dtype=x.dtype, device=dev)
             out = torch.empty((bucket, self.config.num_labels), dtype=torch.float32, device=dev)
             c = self.config.to_c()
 
             def launch():
                 _lib.check(_lib.load().tic_vit_forward(
                     ctypes.byref(c), c_void_p(self._arena.data_ptr()), c_void_p(self._shadow.data_ptr()),
-                    c_void_p(xin.data_ptr()), c_void_p(0), c_int(bucket), c_void_p(ws.data_ptr()), c_i64(ws.numel()),
+                    c_void_p(0 if from_patches else xin.data_ptr()), c_void_p(xin.data_ptr() if from_patches else 0),
+                    c_int(bucket), c_void_p(ws.data_ptr()), c_i64(ws.numel()),
                     c_int(0), c_void_p(out.data_ptr()), _stream(dev)))
 
             launch()  # eager warm-up: one-time function attributes and driver entry points are set outside the capture
@@ -496,8 +499,8 @@ class ViTForImageClassification(nn.Module):
                 launch()
             entry = dict(graph=graph, x=xin, out=out, ws=ws, shadow_ptr=self._shadow.data_ptr(),
                          arena_ptr=self._arena.data_ptr())
-            self._graphs[bucket] = entry
-        entry["x"][:batch].copy_(x)
+            self._graphs[key] = entry
+        entry["x"][:x.shape[0]].copy_(x)
         entry["graph"].replay()
         return entry["out"][:batch].clone()
 

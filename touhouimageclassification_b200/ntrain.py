@@ -204,14 +204,21 @@ def evaluate(lmodule, loader, step: str = "validation_step", device=None, augmen
     return {k: (red[j] / total if total else 0.0) for j, k in enumerate(keys)}
 
 
+LIGHTNING_LAYOUT_VERSION = "2.1.0"   # the checkpoint layout written below is Lightning 2.x's
+
+
 def save_checkpoint(path, lmodule, optimizer, state: FitState):
     """Lightning's checkpoint layout, reduced to what the reference's tooling reads: ``state_dict`` with ``vit.`` keys
     (``load_from_checkpoint``, ``--transform``), ``optimizer_states``, ``epoch`` / ``global_step`` for resuming."""
     import os
     os.makedirs(os.path.dirname(path) or ".", exist_ok=True)
-    torch.save({"epoch": state.epoch, "global_step": state.global_step, "pytorch-lightning_version": "tic_b200",
+    # "pytorch-lightning_version" must parse as a version: Lightning's migrate_checkpoint (load_from_checkpoint,
+    # Trainer(ckpt_path)) runs packaging.version.Version over it. Lightning keys "callbacks" by callback state_key, so the
+    # state of this loop's policies lives under its own key and "callbacks" stays empty (Lightning then starts its
+    # callbacks fresh, which is what it does for any checkpoint written without them).
+    torch.save({"epoch": state.epoch, "global_step": state.global_step, "pytorch-lightning_version": LIGHTNING_LAYOUT_VERSION,
                 "state_dict": lmodule.state_dict(), "optimizer_states": [optimizer.state_dict()], "lr_schedulers": [],
-                "callbacks": state.callbacks_state()}, path)
+                "loops": {}, "callbacks": {}, "tic_callbacks": state.callbacks_state()}, path)
 
 
 def transform_checkpoint(checkpoint_path, out_path):
@@ -247,6 +254,9 @@ def fit(lmodule, train_loader, val_loader, *, max_epochs: int, patience: int = 3
     optimizer = optimizer or lmodule.configure_optimizers()
     rank0 = not (dist.is_available() and dist.is_initialized()) or dist.get_rank() == 0
     fused = isinstance(optimizer, FusedAdamW)
+    if data_parallel is not None and not fused:
+        raise ValueError("data_parallel needs the FusedAdamW optimizer (the gradient exchange runs inside the fused step); "
+                         "a stock optimizer would train every rank on its own shard without any exchange")
     state = FitState()
     if ckpt_path is not None:
         ckpt = torch.load(ckpt_path, map_location="cpu", weights_only=False)
@@ -255,7 +265,7 @@ def fit(lmodule, train_loader, val_loader, *, max_epochs: int, patience: int = 3
             optimizer.load_state_dict(ckpt["optimizer_states"][0])
         state.epoch = int(ckpt.get("epoch", -1))
         state.global_step = int(ckpt.get("global_step", 0))
-        cb = ckpt.get("callbacks") or {}
+        cb = ckpt.get("tic_callbacks") or {}   # absent in a checkpoint written by Lightning itself: policies start fresh
         state.best = [tuple(b) for b in cb.get("best", [])]
         state.periodic = list(cb.get("periodic", []))
         state.best_score = cb.get("best_score")
@@ -264,6 +274,17 @@ def fit(lmodule, train_loader, val_loader, *, max_epochs: int, patience: int = 3
 
     def ckpt_name(epoch, val_acc):
         return os.path.join(checkpoint_dir, f"checkpoint_{train_id}_epoch={epoch:02d}_val_acc={val_acc:.4f}.ckpt")
+
+    if data_parallel is not None and data_parallel.world_size > 1:
+        # the loss gradient is pre-scaled by 1 / (local batch * world) and every bucket is all-reduced once per step: the
+        # ranks must see the same number of equally sized batches (shard with drop_last / equal shard lengths)
+        shape = [len(train_loader), len(getattr(train_loader, "dataset", ())), int(getattr(train_loader, "batch_size", 0) or 0)]
+        shapes = [None] * data_parallel.world_size
+        dist.all_gather_object(shapes, shape)
+        if any(s != shapes[0] for s in shapes):
+            raise ValueError(f"data-parallel fit needs identical shard shapes on every rank (batches, samples, batch size): {shapes}")
+        if augment is not None:   # (seed, global sample index): rank r's i-th local sample of a step is sample r * B + i
+            augment.shard(dist.get_rank(), data_parallel.world_size)
 
     for epoch in range(state.epoch + 1, max_epochs):
         lmodule.train()
