@@ -509,7 +509,7 @@ def run_ours(args):
     inference = None
     if not args.no_inference:
         from touhouimageclassification_b200.augment import IMAGENET_MEAN, IMAGENET_STD
-        from touhouimageclassification_b200.serve import predict_batch_u8
+        from touhouimageclassification_b200.serve import predict_batch, predict_batch_u8
         del trainer
         model._workspaces.clear()            # drop the 46 GB training workspace before the batch-1024 forwards
         torch.cuda.empty_cache()
@@ -557,14 +557,24 @@ def run_ours(args):
             # utils/serve.py:158-230 one image at a time, web/runtime.py:235-251 chunks of <= 64): pinned uint8 256x256
             # thumbnails -> H2D -> resize+normalise+patchify kernel -> engine forward -> softmax/top-1 kernel -> host
             # list of (class, confidence); wall clock around the call, copies inside the timed region
-            inference["e2e"] = dict(api="touhouimageclassification_b200.serve.predict_batch_u8(model, pinned uint8 NHWC "
-                                        "256x256 thumbnails, mean, std) -> host [(class, confidence)]", batches={})
-            for bs in ((1, 8, 64, 1024) if world == 1 else (64, 1024)):
-                u8 = torch.randint(0, 256, (bs, 256, 256, 3), dtype=torch.uint8).pin_memory()
-                ms = time_wall(lambda: predict_batch_u8(model, u8, IMAGENET_MEAN, IMAGENET_STD, None, max_batch_size=1024),
-                               20 if bs <= 64 else 5)
+            from_u8 = S <= 224   # the fused resize+normalise+patchify kernel keeps the output image in shared memory: <= 224
+            inference["e2e"] = dict(api=("touhouimageclassification_b200.serve.predict_batch_u8(model, pinned uint8 NHWC "
+                                         "256x256 thumbnails, mean, std) -> host [(class, confidence)]") if from_u8 else
+                                    ("touhouimageclassification_b200.serve.predict_batch(model, pinned fp32 NCHW preprocessed "
+                                     "images) -> host [(class, confidence)]"), batches={})
+            e2e_sizes = (1, 8, 64, 1024) if S <= 224 else (1, 8, 64, 256)
+            for bs in (e2e_sizes if world == 1 else e2e_sizes[-2:]):
+                if from_u8:
+                    src = torch.randint(0, 256, (bs, 256, 256, 3), dtype=torch.uint8).pin_memory()
+                    fn = lambda: predict_batch_u8(model, src, IMAGENET_MEAN, IMAGENET_STD, None, max_batch_size=1024)
+                else:
+                    src = torch.randn(bs, 3, S, S).pin_memory()
+                    fn = lambda: predict_batch(model, src, None, max_batch_size=1024)
+                ms = time_wall(fn, 20 if bs <= 64 else 5)
                 inference["e2e"]["batches"][str(bs)] = dict(ms=round(ms, 4), img_per_s=round(bs * world / (ms / 1e3), 1),
-                                                            h2d_bytes=u8.numel() * world, d2h_bytes=bs * 8 * world)
+                                                            h2d_bytes=src.numel() * src.element_size() * world,
+                                                            d2h_bytes=bs * 8 * world)
+                del src
             if world == 1:
                 model.set_precision("fp32")        # the reference's no-autocast serving arithmetic (serve.py:99-101)
                 xb = torch.randn(64, 3, S, S, device=dev, generator=g)

@@ -98,6 +98,27 @@ def test_gemm_fused_epilogues():
     assert rel(cs, out.float().sum(0)) < 1e-4
 
 
+@pytest.mark.parametrize("M,N,K", [(197, 1024, 1024), (197, 3072, 1024), (1576, 1024, 4096), (1576, 4096, 1024), (8, 1024, 1024),
+                                   (130, 136, 72), (20000, 1024, 256)])
+def test_gemm_forward_epilogues_small_and_wide_tiles(M, N, K):
+    """The forward epilogues pick between two tile configurations by problem size (CTA pairs with 256 x 256 tiles, or
+    single CTAs with 128 x 128 tiles when the wide tiles would leave most of the machine idle: small-batch inference).
+    Shapes on both sides of the switch, ragged edges included, against fp32 matmuls of the same bf16 operands."""
+    from touhouimageclassification_b200 import ops
+    g = torch.Generator(device=dev).manual_seed(M + N + K)
+    a = (torch.randn(M, K, device=dev, generator=g) * 0.3).bfloat16()
+    b = (torch.randn(N, K, device=dev, generator=g) * 0.1).bfloat16()
+    bias = torch.randn(N, device=dev, generator=g) * 0.1
+    pre = a.float() @ b.float().t() + bias
+    out = ops.gemm_bf16(a, b, bias=bias, epilogue=ops.EPI_BF16)
+    assert rel(out, pre) < 3e-3 and torch.equal(out, pre.bfloat16()) or rel(out.float(), pre.bfloat16().float()) < 1e-3
+    act, dact = ops.gemm_bf16(a, b, bias=bias, epilogue=ops.EPI_BF16_GELU)
+    assert rel(act, F.gelu(pre.bfloat16().float())) < 4e-3
+    res = torch.randn(M, N, device=dev, generator=g)
+    out = ops.gemm_bf16(a, b, bias=bias, aux=res, epilogue=ops.EPI_F32_RESID)
+    assert rel(out, pre.bfloat16().float() + res) < 1e-3
+
+
 def test_gemm_rejects_bad_arguments():
     from touhouimageclassification_b200 import ops, _lib
     a = torch.randn(128, 64, device=dev).bfloat16()

@@ -32,7 +32,8 @@ namespace tic {
 namespace {
 
 constexpr int BM = 128;   // accumulator rows per CTA (one TMEM lane per row)
-constexpr int BN = 256;
+constexpr int BN_WIDE = 256;  // N tile of the CTA-pair configuration (256 x 256 per pair)
+constexpr int BN_SMALL = 128; // N tile of the single-CTA configuration for few-tile problems (128 x 128 per CTA)
 constexpr int BK = 64;
 constexpr int UMMA_K = 16;
 constexpr int ACC_STAGES = 2;
@@ -41,20 +42,19 @@ constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
 // Epilogue warps per CTA: 8 (two per TMEM lane quadrant) everywhere except the GELU forward epilogue, whose ~24
 // instructions per element (value + derivative) need more issue slots than two warps per SM sub-partition deliver inside
 // one tile's MMA time: it runs 12 (three per quadrant, column chunks dealt round-robin) and gives up one operand stage.
-template <int EPI>
-constexpr int epi_warps() { return EPI == kEpiBf16Gelu ? 12 : 8; }
-constexpr int TMEM_COLS = ACC_STAGES * BN;  // 512
+template <int EPI, int BN = BN_WIDE>
+constexpr int epi_warps() { return (EPI == kEpiBf16Gelu && BN == BN_WIDE) ? 12 : 8; }
 constexpr int EPI_STAGE_BYTES = 32 * 32 * 4;  // per epilogue warp: 32 rows x 32 fp32 columns
 
 // NCTA = 1: one CTA computes a 128 x 256 tile.  NCTA = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) computes a
 // 256 x 256 tile with one UMMA M=256: each CTA stages its own 128 A rows and HALF of the B tile (128 of the 256
 // N rows), which halves the L2 -> smem operand traffic per FLOP and frees smem for a deeper ring.
-template <int NCTA, int NEPI = 8>
+template <int NCTA, int NEPI = 8, int BN = BN_WIDE>
 struct Cfg {
   static constexpr int B_ROWS = BN / NCTA;                 // B rows (N) staged per CTA
   static constexpr int B_STAGE_BYTES = B_ROWS * BK * 2;    // 32 KB / 16 KB
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES = NCTA == 2 ? (NEPI > 8 ? 5 : 6) : 4;
+  static constexpr int STAGES = NCTA == 2 ? (NEPI > 8 ? 5 : 6) : (BN == BN_SMALL ? 6 : 4);
   static constexpr int TILE_M = BM * NCTA;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + NEPI * EPI_STAGE_BYTES + 1024 /*align*/ + 512 /*barriers*/;
 };
@@ -76,14 +76,15 @@ struct GemmParams {
   int dynamic;    // 1: one cluster per tile in the grid, running clusters take over not-yet-started ones (cluster launch control)
 };
 
-template <bool A_MN, bool B_MN, int EPI, int NCTA>
-__global__ void __launch_bounds__((epi_warps<EPI>() + 2) * 32, 1)
+template <bool A_MN, bool B_MN, int EPI, int NCTA, int BN>
+__global__ void __launch_bounds__((epi_warps<EPI, BN>() + 2) * 32, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const GemmParams p) {
-  constexpr int NUM_EPI_WARPS = epi_warps<EPI>();
+  constexpr int NUM_EPI_WARPS = epi_warps<EPI, BN>();
+  constexpr int TMEM_COLS = ACC_STAGES * BN;
   constexpr int kTmaWarp = NUM_EPI_WARPS, kMmaWarp = NUM_EPI_WARPS + 1;
   constexpr int kParts = NUM_EPI_WARPS / 4;  // epilogue warps per TMEM lane quadrant
-  using C = Cfg<NCTA, NUM_EPI_WARPS>;
+  using C = Cfg<NCTA, NUM_EPI_WARPS, BN>;
   constexpr int STAGES = C::STAGES;
   constexpr int B_STAGE_BYTES = C::B_STAGE_BYTES;
   constexpr int STAGE_BYTES = C::STAGE_BYTES;
@@ -495,12 +496,24 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   }
 }
 
-constexpr int kNcta = 2;  // CTA pairs (tcgen05 cta_group::2)
+// Few-tile problems (small-batch inference: M = 197 ... a few thousand rows) leave most of the 74 CTA pairs idle with
+// 256 x 256 tiles -- a ViT-L out-projection at batch 8 has 28 tiles. They run the single-CTA configuration instead:
+// 128 x 128 tiles, one per SM, 6-stage ring. It moves twice the operand bytes per FLOP through L2, so it only wins
+// while the wide configuration cannot fill the machine: pick by estimated waves x work per wave.
+inline bool prefer_small_tiles(int M, int N) {
+  const int sms = device_sm_count();
+  const long long wide = static_cast<long long>((M + 255) / 256) * ((N + BN_WIDE - 1) / BN_WIDE);
+  const long long small = static_cast<long long>((M + BM - 1) / BM) * ((N + BN_SMALL - 1) / BN_SMALL);
+  const long long pairs = sms / 2 > 0 ? sms / 2 : 1;
+  const double cost_wide = 2.0 * static_cast<double>((wide + pairs - 1) / pairs);
+  const double cost_small = 1.3 * static_cast<double>((small + sms - 1) / sms);
+  return cost_small < cost_wide;
+}
 
-template <bool A_MN, bool B_MN, int EPI>
+template <bool A_MN, bool B_MN, int EPI, int kNcta = 2, int BN = BN_WIDE>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
-  using C = Cfg<kNcta, epi_warps<EPI>()>;
-  auto kern = gemm_bf16_tcgen05_kernel<A_MN, B_MN, EPI, kNcta>;
+  using C = Cfg<kNcta, epi_warps<EPI, BN>(), BN>;
+  auto kern = gemm_bf16_tcgen05_kernel<A_MN, B_MN, EPI, kNcta, BN>;
   if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), C::SMEM_BYTES, "gemm")) return rc;
   const int m_blocks = (p.M + C::TILE_M - 1) / C::TILE_M, n_blocks = (p.N + BN - 1) / BN;
   const int total = m_blocks * n_blocks * p.splits;
@@ -513,7 +526,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cu
   const int workers = (pl.dynamic || total < max_workers) ? total : max_workers;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(workers * kNcta);
-  cfg.blockDim = dim3((epi_warps<EPI>() + 2) * 32);
+  cfg.blockDim = dim3((epi_warps<EPI, BN>() + 2) * 32);
   cfg.dynamicSmemBytes = C::SMEM_BYTES;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -556,7 +569,8 @@ int gemm_bf16(const void* A, long long lda, bool a_mn, const void* B, long long 
   if (!a_mn) rc = encode_tmap_2d_bf16(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, 64, BM);
   else       rc = encode_tmap_2d_bf16(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 64, BK);
   if (rc) return rc;
-  if (!b_mn) rc = encode_tmap_2d_bf16(&tb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, 64, Cfg<kNcta>::B_ROWS);
+  static_assert(Cfg<2, 8, BN_WIDE>::B_ROWS == 128 && Cfg<1, 8, BN_SMALL>::B_ROWS == 128, "both configurations stage 128 B rows per CTA");
+  if (!b_mn) rc = encode_tmap_2d_bf16(&tb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, 64, 128);
   else       rc = encode_tmap_2d_bf16(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, BK);
   if (rc) return rc;
 
@@ -576,6 +590,15 @@ int gemm_bf16(const void* A, long long lda, bool a_mn, const void* B, long long 
                  stream);
 #define TIC_GEMM_CASE(AMN, BMN, E) \
   if (a_mn == AMN && b_mn == BMN && epilogue == E) return launch<AMN, BMN, E>(ta, tb, p, stream);
+#define TIC_GEMM_CASE_SMALL(E) \
+  if (!a_mn && !b_mn && epilogue == E && small) return launch<false, false, E, 1, BN_SMALL>(ta, tb, p, stream);
+  // forward of a few-tile problem (K-major x K-major, single-CTA 128 x 128 tiles)
+  const bool small = splits == 1 && prefer_small_tiles(M, N);
+  TIC_GEMM_CASE_SMALL(kEpiBf16)
+  TIC_GEMM_CASE_SMALL(kEpiBf16Gelu)
+  TIC_GEMM_CASE_SMALL(kEpiF32Resid)
+  TIC_GEMM_CASE_SMALL(kEpiF32PosEmbed)
+#undef TIC_GEMM_CASE_SMALL
   // forward (K-major x K-major)
   TIC_GEMM_CASE(false, false, kEpiBf16)
   TIC_GEMM_CASE(false, false, kEpiBf16Gelu)

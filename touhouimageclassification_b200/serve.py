@@ -167,7 +167,6 @@ class ReplicaPool:
     request into per-replica chunks, run them concurrently and return the results in request order."""
 
     def __init__(self, model: ViTForImageClassification, devices=None):
-        import copy
         if devices is None:
             devices = [f"cuda:{i}" for i in range(torch.cuda.device_count())]
         if not devices:
@@ -178,7 +177,11 @@ class ReplicaPool:
             if model._arena.device == d:
                 rep = model
             else:
-                rep = copy.deepcopy(model).to(d)
+                # a fresh module from the same config + the same weights (the model's arenas, graphs, workspaces and
+                # locks are per device and are not copied)
+                rep = type(model)(model.config)
+                rep.load_state_dict(model.state_dict(), strict=True)
+                rep = rep.to(d)
                 rep._lock = threading.RLock()
                 rep.set_precision(model.precision)
             self.replicas.append(rep.eval())
