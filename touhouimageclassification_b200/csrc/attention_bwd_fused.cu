@@ -93,6 +93,7 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
 #else
 #define FB_STAMP(slot) do { } while (0)
 #endif
+  pdl_launch_dependents();
   extern __shared__ uint8_t fb_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(fb_smem_raw) + 1023) & ~uintptr_t(1023));
   if (smem + FB_SMEM_USED > fb_smem_raw + FB_SMEM) {  // never observed: the dynamic window starts 1024-byte aligned
@@ -145,6 +146,7 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // the set-up above is independent of the preceding kernel; its outputs are read (and buffers written) below
   if (warp < 8) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(FB_REGS_COMPUTE));
   else asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(FB_REGS_OTHER));
 
@@ -485,8 +487,8 @@ int attention_bwd_fused(const void* q, const void* k, const void* v, long long l
   cudaMallocManaged(&trace, 128 * sizeof(long long));
   for (int i = 0; i < 128; ++i) trace[i] = 0;
 #endif
-  attn_bwd_fused_kernel<<<grid, FB_THREADS, FB_SMEM, stream>>>(
-      tq, tk, tv, tdo, to, tdq, tdk, tdv, lse, bias_grad, bias_mask, N, Nq, H, items, scale, trace);
+  launch_pdl(attn_bwd_fused_kernel, grid, dim3(FB_THREADS), FB_SMEM, stream, tq, tk, tv, tdo, to, tdq, tdk, tdv, lse, bias_grad,
+             bias_mask, N, Nq, H, items, scale, trace);
 #ifdef TIC_ATTN_TRACE
   cudaDeviceSynchronize();
   {

@@ -85,6 +85,7 @@ attn_bwd_long_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
 #define BL_STAMP(slot) do { } while (0)
 #endif
   // N = keys per image; Nq = queries per image (the first Nq tokens; lse / delta are [B, H, Nq])
+  pdl_launch_dependents();
   extern __shared__ uint8_t bl_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(bl_smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sKV = smem;                                         // [2][K tile | V tile]
@@ -150,6 +151,7 @@ attn_bwd_long_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // the set-up above is independent of the preceding kernel; its outputs are read (and buffers written) below
   if (warp < 8) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(BL_REGS_COMPUTE));
   else asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(BL_REGS_OTHER));
 
@@ -590,8 +592,8 @@ int attention_bwd_long(const void* q, const void* k, const void* v, long long ld
   cudaMallocManaged(&trace, 128 * sizeof(long long));
   for (int i = 0; i < 128; ++i) trace[i] = 0;
 #endif
-  attn_bwd_long_kernel<<<grid, BL_THREADS, BL_SMEM, stream>>>(tq, tk, tv, tdo, tdq, tdk, tdv, lse, delta, dq_scratch, bias_grad,
-                                                             bias_mask, N, Nq, H, heads, scale, trace);
+  launch_pdl(attn_bwd_long_kernel, grid, dim3(BL_THREADS), BL_SMEM, stream, tq, tk, tv, tdo, tdq, tdk, tdv, lse, delta, dq_scratch,
+             bias_grad, bias_mask, N, Nq, H, heads, scale, trace);
 #ifdef TIC_ATTN_TRACE
   cudaDeviceSynchronize();
   {

@@ -91,6 +91,7 @@ attn_fwd_fused_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
   // N = keys per item; Nq = queries per item (the first Nq tokens of each image: Nq = N normally, Nq = 1 when only the
   // CLS row of the last encoder layer is needed)
   const int N = N_rt;
+  pdl_launch_dependents();
   extern __shared__ uint8_t ff_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ff_smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sOut = smem + 2 * FF_STAGE_BYTES;
@@ -129,6 +130,7 @@ attn_fwd_fused_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // the set-up above is independent of the preceding kernel; its outputs are read (and buffers written) below
   if (warp < FF_ENGINE_WARPS) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(FF_REGS_ENGINE));
   else asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(FF_REGS_OTHER));
   auto par = [](int u) -> uint32_t { return static_cast<uint32_t>(u >> 1) & 1u; };  // phase parity of unit u's barriers
@@ -384,7 +386,7 @@ int attention_fwd_fused(const void* q, const void* k, const void* v, long long l
   cudaMallocManaged(&trace, 64 * sizeof(long long));
   for (int i = 0; i < 64; ++i) trace[i] = 0;
 #endif
-  kernel<<<grid, FF_THREADS, FF_SMEM, stream>>>(tq, tk, tv, to, lse, N, Nq, H, items, scale, trace);
+  launch_pdl(kernel, grid, dim3(FF_THREADS), FF_SMEM, stream, tq, tk, tv, to, lse, N, Nq, H, items, scale, trace);
 #ifdef TIC_ATTN_TRACE
   cudaDeviceSynchronize();
   {

@@ -52,6 +52,7 @@ attn_fwd_long_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                      const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_o,
                      float* __restrict__ lse, int N, int Nq, int H, int num_items, float scale) {
   // N = keys per image; Nq = queries per image (the first Nq tokens; Nq = 1 for the CLS-only last layer)
+  pdl_launch_dependents();
   extern __shared__ uint8_t fl_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(fl_smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;                                     // [2 stages][2 tiles][128 rows][128 B]
@@ -104,6 +105,7 @@ attn_fwd_long_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // the set-up above is independent of the preceding kernel; its outputs are read (and buffers written) below
 
   if (warp == 8) {
     if (elect_one()) {
@@ -455,7 +457,7 @@ int attention_fwd_long(const void* q, const void* k, const void* v, long long ld
   const int items = B * H * ((nqt + 1) / 2);
   const int num_sms = device_sm_count();
   dim3 grid(items < num_sms ? items : num_sms);
-  attn_fwd_long_kernel<<<grid, FL_THREADS, FL_SMEM, stream>>>(tq, tk, tv, to, lse, N, Nq, H, items, scale);
+  launch_pdl(attn_fwd_long_kernel, grid, dim3(FL_THREADS), FL_SMEM, stream, tq, tk, tv, to, lse, N, Nq, H, items, scale);
   return check_launch("attention_fwd_long");
 }
 

@@ -176,6 +176,8 @@ int vit_forward(const tic_vit_config* c, const float* P32, const void* P16v, con
   const int G = S / 16, N = G * G + 1, Pn = N - 1;
   const int M = B * N;
   const float scale = 0.125f;  // 1 / sqrt(head_dim = 64)
+  // small inference forwards are dominated by launch gaps: overlap each kernel's prologue with its predecessor's tail
+  PdlScope pdl(training == 0 && M <= 8192);
 
   // ---- embeddings: patchify -> projection GEMM (+bias, +pos) -> CLS rows
   const void* patches = patches_in;

@@ -80,6 +80,7 @@ template <bool A_MN, bool B_MN, int EPI, int NCTA, int BN>
 __global__ void __launch_bounds__((epi_warps<EPI, BN>() + 2) * 32, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const GemmParams p) {
+  pdl_launch_dependents();  // programmatic dependent launch: the next kernel's prologue may overlap this kernel
   constexpr int NUM_EPI_WARPS = epi_warps<EPI, BN>();
   constexpr int TMEM_COLS = ACC_STAGES * BN;
   constexpr int kTmaWarp = NUM_EPI_WARPS, kMmaWarp = NUM_EPI_WARPS + 1;
@@ -148,6 +149,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
+  pdl_wait();  // everything above is independent of the preceding kernel; operands and outputs are touched below
 
   // ---- tile sequence of this worker (a CTA or a CTA pair).
   // Static: tiles worker, worker + num_workers, ... of a grid sized to the machine.
@@ -529,13 +531,15 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cu
   cfg.blockDim = dim3((epi_warps<EPI, BN>() + 2) * 32);
   cfg.dynamicSmemBytes = C::SMEM_BYTES;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = kNcta;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, pl);
   if (e != cudaSuccess) return set_error(kErrCuda, "gemm: cudaLaunchKernelEx: %s", cudaGetErrorString(e));
   return check_launch("gemm_bf16_tcgen05");

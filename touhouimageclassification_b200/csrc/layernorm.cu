@@ -20,6 +20,8 @@ ln_fwd_kernel(const float* __restrict__ x, long long ldx, const float* __restric
               const float* __restrict__ beta, float eps, int rows, __nv_bfloat16* __restrict__ y_bf16,
               long long ldy, float* __restrict__ y_f32, long long ldyf, float* __restrict__ mean_out,
               float* __restrict__ rstd_out) {
+  pdl_launch_dependents();
+  pdl_wait();  // every thread, before the early exit below: x comes from the preceding kernel
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * LN_WARPS + warp;
   if (row >= rows) return;
@@ -77,6 +79,7 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long lddy, const float*
               __nv_bfloat16* __restrict__ dx_bf16, long long lddxb, float* __restrict__ dgamma,
               float* __restrict__ dbeta, float* __restrict__ dxsum, int dynamic, int chunk_rows) {
   constexpr int D = VEC * 128;
+  pdl_launch_dependents();
   extern __shared__ float4 ln_smem[];
   float4* sg = ln_smem;                           // [LN_WARPS][VEC * 32] dgamma partials
   float4* sb = ln_smem + LN_WARPS * VEC * 32;     // [LN_WARPS][VEC * 32] dbeta partials
@@ -91,6 +94,7 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long lddy, const float*
     my_b[lane + 32 * i] = make_float4(0.f, 0.f, 0.f, 0.f);
     my_c[lane + 32 * i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
+  pdl_wait();  // the accumulators above needed nothing from the preceding kernel; dy / x / dres below do
   const float4* g4 = reinterpret_cast<const float4*>(gamma);
   // Work is handed out in chunks of chunk_rows rows. Static: chunks blockIdx.x, blockIdx.x + gridDim.x, ...
   // Dynamic: the grid holds one CTA per chunk and a running CTA takes over CTAs that have not started (cluster launch
@@ -234,8 +238,8 @@ int layernorm_fwd(const float* x, long long ldx, const float* gamma, const float
   auto* yb = reinterpret_cast<__nv_bfloat16*>(y_bf16);
 #define TIC_LN_FWD(V)                                                                                              \
   case V:                                                                                                          \
-    ln_fwd_kernel<V><<<grid, LN_WARPS * 32, 0, stream>>>(x, ldx, gamma, beta, eps, rows, yb, ldy, y_f32, ldyf, mean, \
-                                                         rstd);                                                    \
+    launch_pdl(ln_fwd_kernel<V>, dim3(grid), dim3(LN_WARPS * 32), 0, stream, x, ldx, gamma, beta, eps, rows, yb, ldy, \
+               y_f32, ldyf, mean, rstd);                                                                           \
     break;
   switch (D / 128) {
     TIC_LN_FWD(1) TIC_LN_FWD(2) TIC_LN_FWD(3) TIC_LN_FWD(4) TIC_LN_FWD(6) TIC_LN_FWD(8) TIC_LN_FWD(10) TIC_LN_FWD(12)
@@ -272,9 +276,8 @@ int layernorm_bwd(const void* dy_bf16, long long lddy, const float* x, long long
     if (smem > 48 * 1024) {                                                                                       \
       if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(ln_bwd_kernel<V>), smem, "layernorm_bwd")) return rc; \
     }                                                                                                             \
-    ln_bwd_kernel<V><<<grid, LN_WARPS * 32, smem, stream>>>(dyb, lddy, x, ldx, mean, rstd, gamma, dres, lddres, rows, \
-                                                            dx, lddx, dxb, lddxb, dgamma, dbeta, dxsum, dynamic, \
-                                                            chunk_rows);                                          \
+    launch_pdl(ln_bwd_kernel<V>, dim3(grid), dim3(LN_WARPS * 32), smem, stream, dyb, lddy, x, ldx, mean, rstd, gamma, \
+               dres, lddres, rows, dx, lddx, dxb, lddxb, dgamma, dbeta, dxsum, dynamic, chunk_rows);               \
     break;                                                                                                        \
   }
   switch (D / 128) {

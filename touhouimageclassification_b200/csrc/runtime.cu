@@ -13,6 +13,8 @@
 
 #include "tic_internal.cuh"
 
+#include <cstdlib>
+
 namespace tic {
 
 namespace {
@@ -44,6 +46,16 @@ int set_error(int code, const char* fmt, ...) {
 
 std::atomic<long long> g_launches{0};
 long long launch_count() { return g_launches.load(); }
+
+namespace {
+thread_local int g_pdl_depth = 0;
+}
+bool pdl_enabled() {
+  static const bool on = std::getenv("TIC_NO_PDL") == nullptr;
+  return on && g_pdl_depth > 0;
+}
+PdlScope::PdlScope(bool on) : on_(on) { if (on_) ++g_pdl_depth; }
+PdlScope::~PdlScope() { if (on_) --g_pdl_depth; }
 
 int check_launch(const char* what) {
   g_launches.fetch_add(1, std::memory_order_relaxed);

@@ -82,6 +82,11 @@ TIC_DEVINL void gelu_and_grad_fast(float x, float& y, float& g) {
 }
 
 
+// Programmatic dependent launch (see launch_pdl in tic_internal.cuh): let the next kernel of the stream start launching /
+// block until the previous kernel has completed and its memory is visible.
+TIC_DEVINL void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+TIC_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 TIC_DEVINL float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -7,7 +7,10 @@
 namespace tic {
 namespace {
 
-// logits[b, c] = round( sum_d h[b,d] * W[c,d] + bias[c] ); h, W bf16; one CTA per image, warp per class.
+// logits[b, c] = round( sum_d h[b,d] * W[c,d] + bias[c] ); h, W bf16; CTA (b, g) computes classes [8 g, 8 g + 8) of image
+// b, two per warp (one CTA per image walked its 120 classes in 30 dependent steps: 40 us, the longest kernel of a
+// batch-1 forward).
+constexpr int kHeadClassesPerCta = 8;
 __global__ void __launch_bounds__(128)
 head_fwd_kernel(const __nv_bfloat16* __restrict__ h, long long ldh, const __nv_bfloat16* __restrict__ w,
                 const float* __restrict__ bias, int D, int C, int round_out, float* __restrict__ logits) {
@@ -17,7 +20,8 @@ head_fwd_kernel(const __nv_bfloat16* __restrict__ h, long long ldh, const __nv_b
   for (int i = threadIdx.x; i < D / 8; i += blockDim.x) hs[i] = hr[i];
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int c = warp; c < C; c += 4) {
+  const int c_end = min(C, static_cast<int>(blockIdx.y + 1) * kHeadClassesPerCta);
+  for (int c = blockIdx.y * kHeadClassesPerCta + warp; c < c_end; c += 4) {
     const uint4* wr = reinterpret_cast<const uint4*>(w + static_cast<long long>(c) * D);
     float s = 0.f;
     for (int i = lane; i < D / 8; i += 32) {
@@ -186,7 +190,7 @@ int head_fwd(const void* h_bf16, long long ldh, const void* w_bf16, const float*
   if (D % 8 != 0) return set_error(kErrInvalidArg, "head: D=%d must be a multiple of 8", D);
   if (B <= 0) return kOk;
   ProfScope prof("head_fwd", 2.0 * B * D * C, 2.0 * (static_cast<double>(B) * D + static_cast<double>(C) * D), stream);
-  head_fwd_kernel<<<B, 128, D * 2, stream>>>(reinterpret_cast<const __nv_bfloat16*>(h_bf16), ldh,
+  head_fwd_kernel<<<dim3(B, (C + kHeadClassesPerCta - 1) / kHeadClassesPerCta), 128, D * 2, stream>>>(reinterpret_cast<const __nv_bfloat16*>(h_bf16), ldh,
                                              reinterpret_cast<const __nv_bfloat16*>(w_bf16), bias, D, C, round_out,
                                              logits);
   return check_launch("head_fwd");
