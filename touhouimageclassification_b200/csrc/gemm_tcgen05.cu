@@ -39,11 +39,14 @@ constexpr int UMMA_K = 16;
 constexpr int ACC_STAGES = 2;
 constexpr int CLC_STAGES = 4;  // ring of cluster-launch-control responses (tile hand-outs in flight)
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
-// Epilogue warps per CTA: 8 (two per TMEM lane quadrant) everywhere except the GELU forward epilogue, whose ~24
-// instructions per element (value + derivative) need more issue slots than two warps per SM sub-partition deliver inside
-// one tile's MMA time: it runs 12 (three per quadrant, column chunks dealt round-robin) and gives up one operand stage.
+// Epilogue warps per CTA: 8 (two per TMEM lane quadrant) everywhere except the two GELU epilogues (forward: value +
+// derivative, ~24 instructions per element; fc2 dgrad x GELU' + column sums), whose per-chunk dependency chains need
+// more warps per SM sub-partition to fill the issue slots inside one tile's MMA time: they run 16 (four per quadrant, two
+// 32-column chunks each) and give up one operand stage. Measured at M = 50432 (B200, same box): forward 12 -> 16 warps
+// 1176 -> 1191 TFLOP/s, dgrad 8 -> 16 warps 1180 -> 1262; the residual epilogue gets SLOWER with more warps (8: 1360,
+// 12: 1334, 16: 1256 TFLOP/s at K = 4096 -- its auxiliary-operand prefetch registers and the sixth stage matter more).
 template <int EPI, int BN = BN_WIDE>
-constexpr int epi_warps() { return (EPI == kEpiBf16Gelu && BN == BN_WIDE) ? 12 : 8; }
+constexpr int epi_warps() { return ((EPI == kEpiBf16Gelu || EPI == kEpiBf16DGelu) && BN == BN_WIDE) ? 16 : 8; }
 constexpr int EPI_STAGE_BYTES = 32 * 32 * 4;  // per epilogue warp: 32 rows x 32 fp32 columns
 
 // NCTA = 1: one CTA computes a 128 x 256 tile.  NCTA = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) computes a
@@ -377,16 +380,22 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           // a per-row `continue` serialised the rows and left the epilogue latency-bound.
           auto rows = [&](auto save_grad_tag) {
             constexpr bool kSaveGrad = decltype(save_grad_tag)::value;
+            // all eight staged rows are fetched before the math starts: the shared-memory latency is paid once per chunk
+            // instead of once per row (ncu: the first FADD of every row sat on the short scoreboard)
+            float4 av[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int rr = 4 * i + sub_row;
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                           : "=f"(av[i].x), "=f"(av[i].y), "=f"(av[i].z), "=f"(av[i].w)
+                           : "r"(stg_rd + i * 512 + ((ch ^ (rr & 7)) << 4)));
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
               const int row = row0 + 4 * i;
               const bool ok = row < p.M;
               uint8_t* o = po + i * po_step;
-              float4 a;
-              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                           : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w)
-                           : "r"(stg_rd + i * 512 + ((ch ^ (rr & 7)) << 4)));
+              float4 a = av[i];
               a.x += bias.x; a.y += bias.y; a.z += bias.z; a.w += bias.w;
               if constexpr (EPI == kEpiBf16) {
                 const uint2 w = make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
