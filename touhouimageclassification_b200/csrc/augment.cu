@@ -9,8 +9,11 @@
 // The arithmetic contract is bit-exactness against that restatement (oracle/augment_oracle.py): every float32
 // operation below is an explicitly rounded intrinsic (__fmul_rn / __fadd_rn / __fdiv_rn), never a fused multiply-add.
 //
-// One CTA per image. The 224x224x3 uint8 working image lives in shared memory (planar, 147 KB), so the colour ops,
-// which need a whole-image mean for the contrast step, never round-trip through HBM.
+// A cluster of two CTAs per image: each owns half of the output rows (whole 16-row patch bands) and keeps its part of the
+// uint8 working image in shared memory (planar, <= 74 KB), so the colour ops never round-trip through HBM and two CTAs
+// (32 warps) share an SM. The one whole-image quantity, the grey mean of the contrast step, is summed across the pair
+// through distributed shared memory. ToTensor + Normalize of a uint8 pixel takes 256 values per channel: they are
+// tabulated once per CTA with the reference's own rounded operations, so the output passes are table look-ups.
 // Algorithmic HBM traffic per image: <= H*W*3 bytes read (the crop), 196*768*2 = 301056 bytes written.
 #include <cmath>
 
@@ -38,22 +41,51 @@ __device__ __forceinline__ unsigned char to_u8(float x) {  // clamp to [0, 255] 
 }
 __device__ __forceinline__ float clamp01(float x) { return fminf(fmaxf(x, 0.0f), 1.0f); }
 
-__global__ void __launch_bounds__(AUG_THREADS, 1)
+constexpr int AUG_CLUSTER = 2;                                   // CTAs per image
+constexpr int AUG_MAX_ROWS = ((AUG_MAX_SIZE / 16 + 1) / 2) * 16;  // output rows per CTA (112)
+
+// this CTA's and the peer's value of a shared-memory word (distributed shared memory)
+__device__ __forceinline__ int dsmem_read_peer(const int* p, unsigned peer) {
+  unsigned local = static_cast<unsigned>(__cvta_generic_to_shared(p)), remote;
+  int v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(peer));
+  asm volatile("ld.shared::cluster.s32 %0, [%1];" : "=r"(v) : "r"(remote) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(AUG_THREADS, 2)
 augment_patchify_kernel(const unsigned char* __restrict__ images, int H, int W, const int* __restrict__ ints,
                         const float* __restrict__ floats, int size, float m0, float m1, float m2, float s0, float s1,
                         float s2, __nv_bfloat16* __restrict__ patches, unsigned char* __restrict__ pixels_out,
                         float* __restrict__ tensor_out) {
   extern __shared__ __align__(16) unsigned char aug_smem[];
   AugTables* tab = reinterpret_cast<AugTables*>(aug_smem);
-  unsigned char* pix = aug_smem + ((sizeof(AugTables) + 15) / 16) * 16;  // planar [3][size*size]
+  float* lut = reinterpret_cast<float*>(aug_smem + ((sizeof(AugTables) + 15) / 16) * 16);  // [3][256] normalised values
+  unsigned char* pix = reinterpret_cast<unsigned char*>(lut + 3 * 256);                    // planar [3][rows * size]
   __shared__ int gray_sum;
-  const int b = blockIdx.x, tid = threadIdx.x;
+  const unsigned rank = cluster_ctarank();
+  const int b = blockIdx.x / AUG_CLUSTER, tid = threadIdx.x;
   const int* pi = ints + b * 16;
   const float* pf = floats + b * 4;
   const int top = pi[0], left = pi[1], ch = pi[2], cw = pi[3], flip = pi[4];
-  const int npix = size * size;
+  const int G = size / 16;
+  // this CTA's patch bands [g0, g0 + ng) = output rows [y0, y0 + rows)
+  const int g0 = rank == 0 ? 0 : (G + 1) / 2, ng = rank == 0 ? (G + 1) / 2 : G - (G + 1) / 2;
+  const int y0 = g0 * 16, rows = ng * 16;
+  const int npix = rows * size;          // pixels of this CTA
+  const int plane = npix;                // plane pitch of the working image
+  const int npix_image = size * size;
   const unsigned char* src = images + static_cast<long long>(b) * H * W * 3;
   if (tid == 0) gray_sum = 0;
+
+  // ---- 0. ToTensor + Normalize of every uint8 value, per channel: (v / 255 - mean) / std, each operation rounded
+  {
+    const float mean_c[3] = {m0, m1, m2}, std_c[3] = {s0, s1, s2};
+    for (int e = tid; e < 3 * 256; e += AUG_THREADS) {
+      const int c = e >> 8;
+      lut[e] = __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(e & 255), 255.0f), mean_c[c]), std_c[c]);
+    }
+  }
 
   // ---- 1. antialiased-bilinear tap tables (x: dir 0 over crop width, y: dir 1 over crop height)
   for (int e = tid; e < 2 * size; e += AUG_THREADS) {
@@ -86,9 +118,10 @@ augment_patchify_kernel(const unsigned char* __restrict__ images, int H, int W, 
   }
   __syncthreads();
 
-  // ---- 2. resized crop (+ horizontal flip) -> uint8 working image in shared memory
+  // ---- 2. resized crop (+ horizontal flip) -> uint8 working image in shared memory (this CTA's rows)
   for (int p = tid; p < npix; p += AUG_THREADS) {
-    const int yo = p / size, xo = p - yo * size;
+    const int yl = p / size, xo = p - yl * size;
+    const int yo = y0 + yl;
     const int xr = flip ? size - 1 - xo : xo;
     const int lox = tab->lo[0][xr], nx = tab->n[0][xr], loy = tab->lo[1][yo], ny = tab->n[1][yo];
     float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
@@ -107,8 +140,8 @@ augment_patchify_kernel(const unsigned char* __restrict__ images, int H, int W, 
       acc2 = __fadd_rn(acc2, __fmul_rn(r2, wy));
     }
     pix[p] = to_u8(floorf(__fadd_rn(acc0, 0.5f)));
-    pix[npix + p] = to_u8(floorf(__fadd_rn(acc1, 0.5f)));
-    pix[2 * npix + p] = to_u8(floorf(__fadd_rn(acc2, 0.5f)));
+    pix[plane + p] = to_u8(floorf(__fadd_rn(acc1, 0.5f)));
+    pix[2 * plane + p] = to_u8(floorf(__fadd_rn(acc2, 0.5f)));
   }
   // each thread keeps working on its own pixels: no barrier needed until the contrast mean
 
@@ -120,40 +153,41 @@ augment_patchify_kernel(const unsigned char* __restrict__ images, int H, int W, 
         const float f = pf[0];
         for (int p = tid; p < npix; p += AUG_THREADS) {
 #pragma unroll
-          for (int c = 0; c < 3; ++c) pix[c * npix + p] = to_u8(__fmul_rn(static_cast<float>(pix[c * npix + p]), f));
+          for (int c = 0; c < 3; ++c) pix[c * plane + p] = to_u8(__fmul_rn(static_cast<float>(pix[c * plane + p]), f));
         }
-      } else if (op == 1) {  // contrast: blend(x, mean(gray), c)
+      } else if (op == 1) {  // contrast: blend(x, mean(gray), c); the mean is over the WHOLE image: both CTAs of the pair
         int local = 0;
         for (int p = tid; p < npix; p += AUG_THREADS)
-          local += static_cast<int>(gray_floor_f(pix[p], pix[npix + p], pix[2 * npix + p]));
+          local += static_cast<int>(gray_floor_f(pix[p], pix[plane + p], pix[2 * plane + p]));
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
         if ((tid & 31) == 0) atomicAdd(&gray_sum, local);
-        __syncthreads();
-        const float mean = __fdiv_rn(static_cast<float>(gray_sum), static_cast<float>(npix));
+        cluster_sync_all();   // (also a CTA barrier) both partial sums are complete and visible across the pair
+        const int total = gray_sum + dsmem_read_peer(&gray_sum, rank ^ 1u);
+        const float mean = __fdiv_rn(static_cast<float>(total), static_cast<float>(npix_image));
         const float f = pf[1], omf = __fsub_rn(1.0f, f);
         const float mterm = __fmul_rn(mean, omf);
         for (int p = tid; p < npix; p += AUG_THREADS) {
 #pragma unroll
           for (int c = 0; c < 3; ++c)
-            pix[c * npix + p] = to_u8(__fadd_rn(__fmul_rn(static_cast<float>(pix[c * npix + p]), f), mterm));
+            pix[c * plane + p] = to_u8(__fadd_rn(__fmul_rn(static_cast<float>(pix[c * plane + p]), f), mterm));
         }
       } else if (op == 2) {  // saturation: blend(x, gray(x), s)
         const float f = pf[2], omf = __fsub_rn(1.0f, f);
         for (int p = tid; p < npix; p += AUG_THREADS) {
-          const float r = pix[p], g = pix[npix + p], bl = pix[2 * npix + p];
+          const float r = pix[p], g = pix[plane + p], bl = pix[2 * plane + p];
           const float gterm = __fmul_rn(gray_floor_f(r, g, bl), omf);
           pix[p] = to_u8(__fadd_rn(__fmul_rn(r, f), gterm));
-          pix[npix + p] = to_u8(__fadd_rn(__fmul_rn(g, f), gterm));
-          pix[2 * npix + p] = to_u8(__fadd_rn(__fmul_rn(bl, f), gterm));
+          pix[plane + p] = to_u8(__fadd_rn(__fmul_rn(g, f), gterm));
+          pix[2 * plane + p] = to_u8(__fadd_rn(__fmul_rn(bl, f), gterm));
         }
       } else {  // hue: RGB -> HSV, shift h, HSV -> RGB (v2/functional/_color.py:300-400)
         const float hf = pf[3];
         for (int p = tid; p < npix; p += AUG_THREADS) {
           const float inv255 = 0.00392156862745098f;
           const float r = __fmul_rn(static_cast<float>(pix[p]), inv255);
-          const float g = __fmul_rn(static_cast<float>(pix[npix + p]), inv255);
-          const float bl = __fmul_rn(static_cast<float>(pix[2 * npix + p]), inv255);
+          const float g = __fmul_rn(static_cast<float>(pix[plane + p]), inv255);
+          const float bl = __fmul_rn(static_cast<float>(pix[2 * plane + p]), inv255);
           const float maxc = fmaxf(fmaxf(r, g), bl), minc = fminf(fminf(r, g), bl);
           const bool eqc = maxc == minc;
           const float cr = __fsub_rn(maxc, minc);
@@ -189,8 +223,8 @@ augment_patchify_kernel(const unsigned char* __restrict__ images, int H, int W, 
             default: ro = v; go = pp; bo = q; break;
           }
           pix[p] = static_cast<unsigned char>(__fmul_rn(ro, 255.999f));
-          pix[npix + p] = static_cast<unsigned char>(__fmul_rn(go, 255.999f));
-          pix[2 * npix + p] = static_cast<unsigned char>(__fmul_rn(bo, 255.999f));
+          pix[plane + p] = static_cast<unsigned char>(__fmul_rn(go, 255.999f));
+          pix[2 * plane + p] = static_cast<unsigned char>(__fmul_rn(bo, 255.999f));
         }
       }
     }
@@ -200,55 +234,51 @@ augment_patchify_kernel(const unsigned char* __restrict__ images, int H, int W, 
   const int gray = pi[9], ei = pi[10], ej = pi[11], eh = pi[12], ew = pi[13];
   if (gray || (eh > 0 && ew > 0) || pixels_out != nullptr) {
     for (int p = tid; p < npix; p += AUG_THREADS) {
-      unsigned char r = pix[p], g = pix[npix + p], bl = pix[2 * npix + p];
+      unsigned char r = pix[p], g = pix[plane + p], bl = pix[2 * plane + p];
       if (gray) r = g = bl = static_cast<unsigned char>(gray_floor_f(r, g, bl));
-      const int y = p / size, x = p - y * size;
+      const int yl = p / size, x = p - yl * size;
+      const int y = y0 + yl;
       if (y >= ei && y < ei + eh && x >= ej && x < ej + ew) r = g = bl = 0;
-      pix[p] = r; pix[npix + p] = g; pix[2 * npix + p] = bl;
+      pix[p] = r; pix[plane + p] = g; pix[2 * plane + p] = bl;
       if (pixels_out != nullptr) {
-        unsigned char* o = pixels_out + (static_cast<long long>(b) * npix + p) * 3;
+        unsigned char* o = pixels_out + (static_cast<long long>(b) * npix_image + y0 * size + p) * 3;
         o[0] = r; o[1] = g; o[2] = bl;
       }
     }
   }
   __syncthreads();
 
-  // ---- 5. ToTensor (/255), Normalize, bf16, patch rows with K ordered (c, py, px); 16-byte stores
-  const int G = size / 16;
-  const float mean_c[3] = {m0, m1, m2}, std_c[3] = {s0, s1, s2};
+  // ---- 5. ToTensor (/255), Normalize (table look-ups), bf16, patch rows with K ordered (c, py, px); 16-byte stores
   if (tensor_out != nullptr) {  // the fp32 [3, size, size] tensor the reference's Dataset yields (what CutMix / MixUp blend)
-    float* to = tensor_out + static_cast<long long>(b) * 3 * npix;
+    float* to = tensor_out + static_cast<long long>(b) * 3 * npix_image + y0 * size;
     for (int e = tid; e < 3 * npix / 4; e += AUG_THREADS) {
       const int c = (e * 4) / npix;  // npix is a multiple of 256: a group of four never straddles a plane
-      const unsigned int raw = *reinterpret_cast<const unsigned int*>(pix + e * 4);
-      float4 v;
-      v.x = __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(raw & 0xffu), 255.0f), mean_c[c]), std_c[c]);
-      v.y = __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>((raw >> 8) & 0xffu), 255.0f), mean_c[c]), std_c[c]);
-      v.z = __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>((raw >> 16) & 0xffu), 255.0f), mean_c[c]), std_c[c]);
-      v.w = __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(raw >> 24), 255.0f), mean_c[c]), std_c[c]);
-      *reinterpret_cast<float4*>(to + e * 4) = v;
+      const int q = e * 4 - c * npix;
+      const unsigned int raw = *reinterpret_cast<const unsigned int*>(pix + c * plane + q);
+      const float* l = lut + c * 256;
+      *reinterpret_cast<float4*>(to + static_cast<long long>(c) * npix_image + q) =
+          make_float4(l[raw & 0xffu], l[(raw >> 8) & 0xffu], l[(raw >> 16) & 0xffu], l[raw >> 24]);
     }
   }
-  if (patches == nullptr) return;
-  __nv_bfloat16* out = patches + static_cast<long long>(b) * G * G * 768;
-  for (int e = tid; e < G * G * 96; e += AUG_THREADS) {
-    const int row = e / 96, chunk = e - row * 96;
-    const int k = chunk * 8;
-    const int c = k >> 8, py = (k & 255) >> 4, px = k & 15;
-    const int gy = row / G, gx = row - gy * G;
-    const unsigned char* sp = pix + c * npix + (gy * 16 + py) * size + gx * 16 + px;
-    const uint2 raw = *reinterpret_cast<const uint2*>(sp);
-    float v[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const unsigned int byte = ((j < 4 ? raw.x : raw.y) >> (8 * (j & 3))) & 0xffu;
-      v[j] = __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(byte), 255.0f), mean_c[c]), std_c[c]);
+  if (patches != nullptr) {
+    __nv_bfloat16* out = patches + (static_cast<long long>(b) * G + g0) * G * 768;
+    for (int e = tid; e < ng * G * 96; e += AUG_THREADS) {
+      const int row = e / 96, chunk = e - row * 96;   // row = local patch index (band-major)
+      const int k = chunk * 8;
+      const int c = k >> 8, py = (k & 255) >> 4, px = k & 15;
+      const int gy = row / G, gx = row - gy * G;
+      const unsigned char* sp = pix + c * plane + (gy * 16 + py) * size + gx * 16 + px;
+      const uint2 raw = *reinterpret_cast<const uint2*>(sp);
+      const float* l = lut + c * 256;
+      uint4 w;
+      w.x = pack_bf16x2(l[raw.x & 0xffu], l[(raw.x >> 8) & 0xffu]);
+      w.y = pack_bf16x2(l[(raw.x >> 16) & 0xffu], l[raw.x >> 24]);
+      w.z = pack_bf16x2(l[raw.y & 0xffu], l[(raw.y >> 8) & 0xffu]);
+      w.w = pack_bf16x2(l[(raw.y >> 16) & 0xffu], l[raw.y >> 24]);
+      *reinterpret_cast<uint4*>(out + static_cast<long long>(row) * 768 + k) = w;
     }
-    uint4 w;
-    w.x = pack_bf16x2(v[0], v[1]); w.y = pack_bf16x2(v[2], v[3]);
-    w.z = pack_bf16x2(v[4], v[5]); w.w = pack_bf16x2(v[6], v[7]);
-    *reinterpret_cast<uint4*>(out + static_cast<long long>(row) * 768 + k) = w;
   }
+  cluster_sync_all();  // neither CTA of the pair exits while the other may still read its grey sum
 }
 
 // ---------------------------------------------------------------------------------------------- host sampler
@@ -352,16 +382,32 @@ int augment_patchify(const void* images_u8, int B, int H, int W, const int* ints
   // tap tables hold at most AUG_MAX_TAPS taps: support = max(in/out, 1) must be <= 3.5
   if (H > 3 * size || W > 3 * size)
     return set_error(kErrUnsupported, "augment_patchify: source %dx%d is more than 3x the output size", H, W);
-  const int smem = static_cast<int>((sizeof(AugTables) + 15) / 16 * 16) + 3 * size * size;
+  const int lut_bytes = 3 * 256 * 4;
+  const int rows = ((size / 16 + 1) / 2) * 16;   // output rows of the larger half
+  const int smem = static_cast<int>((sizeof(AugTables) + 15) / 16 * 16) + lut_bytes + 3 * rows * size;
   if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(augment_patchify_kernel),
-                                   static_cast<int>((sizeof(AugTables) + 15) / 16 * 16) + 3 * AUG_MAX_SIZE * AUG_MAX_SIZE,
+                                   static_cast<int>((sizeof(AugTables) + 15) / 16 * 16) + lut_bytes +
+                                       3 * AUG_MAX_ROWS * AUG_MAX_SIZE,
                                    "augment_patchify"))
     return rc;
   ProfScope prof("augment_patchify", 0.0, static_cast<double>(B) * (static_cast<double>(H) * W * 3 + (size / 16) * (size / 16) * 768.0 * 2), stream);
-  augment_patchify_kernel<<<B, AUG_THREADS, smem, stream>>>(
-      reinterpret_cast<const unsigned char*>(images_u8), H, W, ints_dev, floats_dev, size, mean3_host[0], mean3_host[1],
-      mean3_host[2], std3_host[0], std3_host[1], std3_host[2], reinterpret_cast<__nv_bfloat16*>(patches_bf16),
-      reinterpret_cast<unsigned char*>(pixels_out_u8), tensor_out_f32);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(B * AUG_CLUSTER);
+  cfg.blockDim = dim3(AUG_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = AUG_CLUSTER;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, augment_patchify_kernel, reinterpret_cast<const unsigned char*>(images_u8), H, W,
+                                     ints_dev, floats_dev, size, mean3_host[0], mean3_host[1], mean3_host[2], std3_host[0],
+                                     std3_host[1], std3_host[2], reinterpret_cast<__nv_bfloat16*>(patches_bf16),
+                                     reinterpret_cast<unsigned char*>(pixels_out_u8), tensor_out_f32);
+  if (e != cudaSuccess) return set_error(kErrCuda, "augment_patchify: cudaLaunchKernelEx: %s", cudaGetErrorString(e));
   return check_launch("augment_patchify");
 }
 

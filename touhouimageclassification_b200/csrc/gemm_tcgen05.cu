@@ -6,8 +6,8 @@
 // intermediate :290-299, output :305-312, patch projection :151-167) and their autograd
 // backward GEMMs (cuBLASLt in the reference's stack).
 //
-// One CTA pair (cluster of 2, tcgen05 cta_group::2) per two SMs computes 256 x 256 tiles; 10 warps per CTA (14 for the
-// GELU epilogue):
+// One CTA pair (cluster of 2, tcgen05 cta_group::2) per two SMs computes 256 x 256 tiles; 10 warps per CTA (18 for the
+// two GELU epilogues). Few-tile problems run single CTAs with 128 x 128 tiles instead (prefer_small_tiles below):
 //   warps 0-7  epilogue   (TMEM -> registers -> fused math -> global), 2 warps per TMEM lane quadrant
 //   warp  8    TMA producer (one elected lane) + tile scheduler of the pair (leader CTA)
 //   warp  9    MMA issuer  (one elected lane, leader CTA) + TMEM allocator
