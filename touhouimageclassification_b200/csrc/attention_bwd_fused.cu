@@ -171,6 +171,17 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       uint32_t ph_p = 0, use_acc = 0, use_vk = 0;  // ph_p: bit b = parity of the next completion of bar_p[b]
       issue_loads(blockIdx.x);
       for (int it = 0, item = blockIdx.x; item < num_items; ++it, item += gridDim.x) {
+        // The operand buffers are single (the SM's shared memory holds one head), so the next item's loads can only be
+        // issued when this item's last MMA has completed -- but its addresses are known now: pull the five boxes into L2
+        // so that those loads pay L2 latency, not DRAM latency, on the critical path between two items.
+        if (item + static_cast<int>(gridDim.x) < num_items) {
+          const int nx = item + gridDim.x, nh = nx % H, nb = nx / H;
+          tma_prefetch_l2_3d(&tm_k, nh * FB_HD, 0, nb);
+          tma_prefetch_l2_3d(&tm_q, nh * FB_HD, 0, nb);
+          tma_prefetch_l2_3d(&tm_do, nh * FB_HD, 0, nb);
+          tma_prefetch_l2_3d(&tm_o, nh * FB_HD, 0, nb);
+          tma_prefetch_l2_3d(&tm_v, nh * FB_HD, 0, nb);
+        }
         auto issue_scores = [&](int j) {
           const int kt = j >= nqb ? 1 : 0, qb = j - kt * nqb, buf = j & 1;
           const int w = qb == nqb - 1 ? w_last : 64;

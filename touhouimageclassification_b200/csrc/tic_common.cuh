@@ -175,6 +175,14 @@ TIC_DEVINL void tma_load_3d(void* smem_dst, const void* desc, uint64_t* bar, int
         "r"(c2)
       : "memory");
 }
+// Pull a 3-D box towards L2 without a destination in shared memory: a later tma_load_3d of the same box then pays L2
+// latency instead of DRAM latency (used where the shared-memory destination is still occupied when the address is known).
+TIC_DEVINL void tma_prefetch_l2_3d(const void* desc, int32_t c0, int32_t c1, int32_t c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(
+                   reinterpret_cast<uint64_t>(desc)),
+               "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 TIC_DEVINL void tma_store_2d(const void* desc, const void* smem_src, int32_t c0, int32_t c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                :
