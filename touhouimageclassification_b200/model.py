@@ -217,6 +217,7 @@ class ViTForImageClassification(nn.Module):
         self.graph_max_batch = 64
         self.graph_buckets = (1, 2, 4, 8, 16, 32, 64)
         self._graphs = {}
+        self._capture_stream = None
 
     # ---- structure ------------------------------------------------------------------------------
     def _build_tree(self, params):
@@ -495,7 +496,11 @@ class ViTForImageClassification(nn.Module):
             graph = torch.cuda.CUDAGraph()
             # thread_local: another thread of the process (a DataLoader pin-memory thread, a second replica) may call
             # cudaHostAlloc / cudaMalloc while this one captures; the default 'global' mode would fail the capture
-            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+            # an explicit capture stream ON THIS DEVICE: torch.cuda.graph's default one is a class-level singleton created
+            # on whichever device captured first, so a replica on another GPU would capture an empty graph
+            if self._capture_stream is None or self._capture_stream.device != dev:
+                self._capture_stream = torch.cuda.Stream(device=dev)
+            with torch.cuda.graph(graph, stream=self._capture_stream, capture_error_mode="thread_local"):
                 launch()
             entry = dict(graph=graph, x=xin, out=out, ws=ws, shadow_ptr=self._shadow.data_ptr(),
                          arena_ptr=self._arena.data_ptr())
