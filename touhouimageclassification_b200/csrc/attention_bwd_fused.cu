@@ -147,11 +147,107 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();  // the set-up above is independent of the preceding kernel; its outputs are read (and buffers written) below
-  if (warp < 8) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(FB_REGS_COMPUTE));
-  else asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(FB_REGS_OTHER));
 
   // Persistent: this CTA walks the (image, head) items blockIdx.x, blockIdx.x + gridDim.x, ... The loads of item i+1
   // are issued as soon as the last MMA of item i has completed, i.e. under the final accumulator drain of item i.
+  // setmaxnreg sits INSIDE each side of the role dispatch: ptxas budgets registers for the code a setmaxnreg dominates
+  // (placed before the dispatch, every role was compiled under the kernel-wide figure and the compute loop spilled)
+  if (warp < 8) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(FB_REGS_COMPUTE));
+    // ------------------------------------------------------------------------------------ compute warps
+    const int quad = warp & 3, half = warp >> 2;
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    const float c2 = scale * FB_LOG2E;
+    const int r = quad * 32 + lane;  // row within the 128-row tile
+    const uint32_t stage_row = smem_u32(sStage) + r * 128;
+    const int sw = r & 7;
+    const int t = threadIdx.x;       // 0..255: the query whose delta / logsumexp this thread prepares
+    const uint32_t aL = smem_u32(sL), aD = smem_u32(sD);
+    const uint32_t ro = smem_u32(sO) + t * 128, rd = smem_u32(sDO) + t * 128;
+    uint32_t ph_s = 0;  // bit b = parity of the next completion of bar_s[b]
+    auto load_lse = [&](int item) -> float {  // per-query logsumexp, +inf past N: exp2(-inf) = 0
+      return (item < num_items && t < Nq) ? __ldg(lse + static_cast<long long>(item) * Nq + t) : INFINITY;
+    };
+    float L_next = load_lse(blockIdx.x);
+    for (int it = 0, item = blockIdx.x; item < num_items; ++it, item += gridDim.x) {
+      const int h = item % H, b = item / H;
+#define FB_CSTAMP(slot) do { if (threadIdx.x == 0) FB_STAMP(slot); } while (0)
+      FB_CSTAMP(0);
+      {
+        // delta[q] = sum_d dO[q, d] * O[q, d], one query row per thread, both rows read from swizzled shared memory
+        mbar_wait(&bar_load[1], it & 1);
+        FB_CSTAMP(1);
+        // four independent partial sums: one 64-long FMA chain kept this pass (which sits on the path between two heads)
+        // waiting on its own latency
+        float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint32_t off = static_cast<uint32_t>((i ^ (t & 7)) << 4);
+          const uint4 a = ld_shared_v4(ro + off), g = ld_shared_v4(rd + off);
+          d0 = fmaf(bf16_lo(a.x), bf16_lo(g.x), d0); d1 = fmaf(bf16_hi(a.x), bf16_hi(g.x), d1);
+          d2 = fmaf(bf16_lo(a.y), bf16_lo(g.y), d2); d3 = fmaf(bf16_hi(a.y), bf16_hi(g.y), d3);
+          d0 = fmaf(bf16_lo(a.z), bf16_lo(g.z), d0); d1 = fmaf(bf16_hi(a.z), bf16_hi(g.z), d1);
+          d2 = fmaf(bf16_lo(a.w), bf16_lo(g.w), d2); d3 = fmaf(bf16_hi(a.w), bf16_hi(g.w), d3);
+        }
+        const float dsum = (d0 + d1) + (d2 + d3);
+        sL[t] = L_next * FB_LOG2E;  // log2 domain (L_next was loaded under the previous item's final drain)
+        sD[t] = dsum;    // rows past N are zero-filled by TMA: delta = 0
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        FB_CSTAMP(2);
+      }
+      for (int j = 0; j < J; ++j) {
+        const int kt = j >= nqb ? 1 : 0, qb = j - kt * nqb, buf = j & 1;
+        const int w = qb == nqb - 1 ? w_last : 64;
+        const bool quad_active = kt * 128 + quad * 32 < N;
+        const bool row_valid = kt * 128 + r < N;
+        mbar_wait(&bar_s[buf], (ph_s >> buf) & 1);
+        FB_CSTAMP(4 + 3 * j);
+        ph_s ^= 1u << buf;
+        tc_fence_after();
+        if (quad_active && half * 32 < w) {
+          uint32_t s[32], dp[32];
+          tmem_ld_32x32b_x32(lane_addr + buf * 64 + half * 32, s);
+          tmem_ld_32x32b_x32(lane_addr + FB_COL_DP + buf * 64 + half * 32, dp);
+          tmem_ld_wait();
+          const uint32_t L4 = aL + (qb * 64 + half * 32) * 4, D4 = aD + (qb * 64 + half * 32) * 4;
+          uint32_t pw[16], dw[16];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 Lq = ld_shared_f4(L4 + 16 * i), Dq = ld_shared_f4(D4 + 16 * i);
+            const float p0 = ex2_approx(fmaf(__uint_as_float(s[4 * i + 0]), c2, -Lq.x));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(s[4 * i + 1]), c2, -Lq.y));
+            const float p2 = ex2_approx(fmaf(__uint_as_float(s[4 * i + 2]), c2, -Lq.z));
+            const float p3 = ex2_approx(fmaf(__uint_as_float(s[4 * i + 3]), c2, -Lq.w));
+            pw[2 * i] = pack_bf16x2(p0, p1);
+            pw[2 * i + 1] = pack_bf16x2(p2, p3);
+            dw[2 * i] = pack_bf16x2(p0 * (__uint_as_float(dp[4 * i + 0]) - Dq.x), p1 * (__uint_as_float(dp[4 * i + 1]) - Dq.y));
+            dw[2 * i + 1] = pack_bf16x2(p2 * (__uint_as_float(dp[4 * i + 2]) - Dq.z), p3 * (__uint_as_float(dp[4 * i + 3]) - Dq.w));
+          }
+          tmem_st_32x32b_x16(lane_addr + buf * 64 + half * 32, pw);
+          tmem_st_32x32b_x16(lane_addr + FB_COL_DP + buf * 64 + half * 32, dw);
+          // dS^T row -> staging tile of this query tile (chunk = 64-query block), zero for key rows past N so that the
+          // dQ product never sees a non-finite value against the zero-filled K rows
+          const uint32_t dst = stage_row + (nqb <= 2 ? (kt & 1) : (qb >> 1)) * FB_STAGE_BYTES + (qb & 1) * 16384;
+#pragma unroll
+          for (int pc = 0; pc < 4; ++pc) {
+            const uint32_t a = dst + (((half * 4 + pc) ^ sw) << 4);
+            if (row_valid) st_shared_v4(a, dw[4 * pc], dw[4 * pc + 1], dw[4 * pc + 2], dw[4 * pc + 3]);
+            else st_shared_v4(a, 0u, 0u, 0u, 0u);
+          }
+          tmem_st_wait();
+          fence_proxy_async();
+        }
+        FB_CSTAMP(5 + 3 * j);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_p[buf]);
+        FB_CSTAMP(6 + 3 * j);
+
+        if (j == J - 1) L_next = load_lse(item + gridDim.x);  // in flight across the item boundary
+      }
+    }
+  } else {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(FB_REGS_OTHER));
   if (warp == 8) {
     if (elect_one()) {  // one issuing thread on the uniform datapath (a lane == 0 test costs ~45 clk per MMA)
       // ---------------------------------------------------------------------------------- TMA + MMA issue loop
@@ -263,96 +359,6 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       }
     }
     __syncwarp();
-  } else if (warp < 8) {
-    // ------------------------------------------------------------------------------------ compute warps
-    const int quad = warp & 3, half = warp >> 2;
-    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
-    const float c2 = scale * FB_LOG2E;
-    const int r = quad * 32 + lane;  // row within the 128-row tile
-    const uint32_t stage_row = smem_u32(sStage) + r * 128;
-    const int sw = r & 7;
-    const int t = threadIdx.x;       // 0..255: the query whose delta / logsumexp this thread prepares
-    const uint32_t aL = smem_u32(sL), aD = smem_u32(sD);
-    const uint32_t ro = smem_u32(sO) + t * 128, rd = smem_u32(sDO) + t * 128;
-    uint32_t ph_s = 0;  // bit b = parity of the next completion of bar_s[b]
-    auto load_lse = [&](int item) -> float {  // per-query logsumexp, +inf past N: exp2(-inf) = 0
-      return (item < num_items && t < Nq) ? __ldg(lse + static_cast<long long>(item) * Nq + t) : INFINITY;
-    };
-    float L_next = load_lse(blockIdx.x);
-    for (int it = 0, item = blockIdx.x; item < num_items; ++it, item += gridDim.x) {
-      const int h = item % H, b = item / H;
-#define FB_CSTAMP(slot) do { if (threadIdx.x == 0) FB_STAMP(slot); } while (0)
-      FB_CSTAMP(0);
-      {
-        // delta[q] = sum_d dO[q, d] * O[q, d], one query row per thread, both rows read from swizzled shared memory
-        mbar_wait(&bar_load[1], it & 1);
-        FB_CSTAMP(1);
-        float dsum = 0.f;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const uint32_t off = static_cast<uint32_t>((i ^ (t & 7)) << 4);
-          const uint4 a = ld_shared_v4(ro + off), g = ld_shared_v4(rd + off);
-          dsum = fmaf(bf16_lo(a.x), bf16_lo(g.x), dsum); dsum = fmaf(bf16_hi(a.x), bf16_hi(g.x), dsum);
-          dsum = fmaf(bf16_lo(a.y), bf16_lo(g.y), dsum); dsum = fmaf(bf16_hi(a.y), bf16_hi(g.y), dsum);
-          dsum = fmaf(bf16_lo(a.z), bf16_lo(g.z), dsum); dsum = fmaf(bf16_hi(a.z), bf16_hi(g.z), dsum);
-          dsum = fmaf(bf16_lo(a.w), bf16_lo(g.w), dsum); dsum = fmaf(bf16_hi(a.w), bf16_hi(g.w), dsum);
-        }
-        sL[t] = L_next * FB_LOG2E;  // log2 domain (L_next was loaded under the previous item's final drain)
-        sD[t] = dsum;    // rows past N are zero-filled by TMA: delta = 0
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        FB_CSTAMP(2);
-      }
-      for (int j = 0; j < J; ++j) {
-        const int kt = j >= nqb ? 1 : 0, qb = j - kt * nqb, buf = j & 1;
-        const int w = qb == nqb - 1 ? w_last : 64;
-        const bool quad_active = kt * 128 + quad * 32 < N;
-        const bool row_valid = kt * 128 + r < N;
-        mbar_wait(&bar_s[buf], (ph_s >> buf) & 1);
-        FB_CSTAMP(4 + 3 * j);
-        ph_s ^= 1u << buf;
-        tc_fence_after();
-        if (quad_active && half * 32 < w) {
-          uint32_t s[32], dp[32];
-          tmem_ld_32x32b_x32(lane_addr + buf * 64 + half * 32, s);
-          tmem_ld_32x32b_x32(lane_addr + FB_COL_DP + buf * 64 + half * 32, dp);
-          tmem_ld_wait();
-          const uint32_t L4 = aL + (qb * 64 + half * 32) * 4, D4 = aD + (qb * 64 + half * 32) * 4;
-          uint32_t pw[16], dw[16];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float4 Lq = ld_shared_f4(L4 + 16 * i), Dq = ld_shared_f4(D4 + 16 * i);
-            const float p0 = ex2_approx(fmaf(__uint_as_float(s[4 * i + 0]), c2, -Lq.x));
-            const float p1 = ex2_approx(fmaf(__uint_as_float(s[4 * i + 1]), c2, -Lq.y));
-            const float p2 = ex2_approx(fmaf(__uint_as_float(s[4 * i + 2]), c2, -Lq.z));
-            const float p3 = ex2_approx(fmaf(__uint_as_float(s[4 * i + 3]), c2, -Lq.w));
-            pw[2 * i] = pack_bf16x2(p0, p1);
-            pw[2 * i + 1] = pack_bf16x2(p2, p3);
-            dw[2 * i] = pack_bf16x2(p0 * (__uint_as_float(dp[4 * i + 0]) - Dq.x), p1 * (__uint_as_float(dp[4 * i + 1]) - Dq.y));
-            dw[2 * i + 1] = pack_bf16x2(p2 * (__uint_as_float(dp[4 * i + 2]) - Dq.z), p3 * (__uint_as_float(dp[4 * i + 3]) - Dq.w));
-          }
-          tmem_st_32x32b_x16(lane_addr + buf * 64 + half * 32, pw);
-          tmem_st_32x32b_x16(lane_addr + FB_COL_DP + buf * 64 + half * 32, dw);
-          // dS^T row -> staging tile of this query tile (chunk = 64-query block), zero for key rows past N so that the
-          // dQ product never sees a non-finite value against the zero-filled K rows
-          const uint32_t dst = stage_row + (nqb <= 2 ? (kt & 1) : (qb >> 1)) * FB_STAGE_BYTES + (qb & 1) * 16384;
-#pragma unroll
-          for (int pc = 0; pc < 4; ++pc) {
-            const uint32_t a = dst + (((half * 4 + pc) ^ sw) << 4);
-            if (row_valid) st_shared_v4(a, dw[4 * pc], dw[4 * pc + 1], dw[4 * pc + 2], dw[4 * pc + 3]);
-            else st_shared_v4(a, 0u, 0u, 0u, 0u);
-          }
-          tmem_st_wait();
-          fence_proxy_async();
-        }
-        FB_CSTAMP(5 + 3 * j);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bar_p[buf]);
-        FB_CSTAMP(6 + 3 * j);
-
-        if (j == J - 1) L_next = load_lse(item + gridDim.x);  // in flight across the item boundary
-      }
-    }
   }
   if (warp > 8 && warp < 13) {
     // ------------------------------------------------------------------------------------ drain warps
@@ -452,6 +458,7 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     }
     if (lane == 0) tma_store_wait_read<0>();  // the staging tiles must outlive the last TMA stores
   }
+  }  // roles other than the compute warps
   tc_fence_before();
   __syncthreads();
   tc_fence_after();

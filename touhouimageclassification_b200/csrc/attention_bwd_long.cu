@@ -152,9 +152,85 @@ attn_bwd_long_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();  // the set-up above is independent of the preceding kernel; its outputs are read (and buffers written) below
-  if (warp < 8) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(BL_REGS_COMPUTE));
-  else asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(BL_REGS_OTHER));
 
+  // setmaxnreg sits INSIDE each side of the role dispatch: ptxas budgets registers for the code a setmaxnreg dominates
+  // (placed before the dispatch, every role was compiled under the kernel-wide figure and the compute loop spilled)
+  if (warp < 8) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(BL_REGS_COMPUTE));
+    // -------------------------------------------------------------------------------------- compute warps
+    const int quad = warp & 3, half = warp >> 2;
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    const float c2 = scale * BL_LOG2E;
+    const int r = quad * 32 + lane;  // key row within the 128-row tile
+    const uint32_t stage_row = smem_u32(sStage) + r * 128;
+    const int sw = r & 7;
+    const uint32_t aL = smem_u32(sL), aD = smem_u32(sD);
+    uint32_t ph_s = 0;  // bit b = parity of the next completion of bar_s[b]
+    int g0 = 0, tiles0 = 0;
+    for (int it = 0; it < num_its; ++it) {
+      const int kt = it % nkt;
+      const int sb = it & 1;
+      const uint32_t aLi = aL + sb * BL_NQ_MAX * 4, aDi = aD + sb * BL_NQ_MAX * 4;
+      mbar_wait(&ld_full[sb], (it >> 1) & 1);
+      const bool quad_active = kt * 128 + quad * 32 < N;
+      const bool row_valid = kt * 128 + r < N;
+      for (int j = 0; j < J; ++j) {
+        const int buf = (g0 + j) & 1;
+        const int w = j == J - 1 ? w_last : 64;
+        const int tile = tiles0 + (j >> 1);
+        if (threadIdx.x == 0) BL_STAMP(3 * j);
+        mbar_wait(&bar_s[buf], (ph_s >> buf) & 1);
+        if (threadIdx.x == 0) BL_STAMP(3 * j + 1);
+        ph_s ^= 1u << buf;
+        tc_fence_after();
+#ifdef TIC_EXP_NO_ELEMENTWISE  // development experiment: the tensor / barrier chain alone (results are garbage)
+        if (false) {
+#else
+        if (quad_active && half * 32 < w) {
+#endif
+          uint32_t s[32], dp[32];
+          tmem_ld_32x32b_x32(lane_addr + buf * 64 + half * 32, s);
+          tmem_ld_32x32b_x32(lane_addr + BL_COL_DP + buf * 64 + half * 32, dp);
+          tmem_ld_wait();
+          const uint32_t L4 = aLi + (j * 64 + half * 32) * 4, D4 = aDi + (j * 64 + half * 32) * 4;
+          uint32_t pw[16], dw[16];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 Lq = bl_ld_shared_f4(L4 + 16 * i), Dq = bl_ld_shared_f4(D4 + 16 * i);
+            const float p0 = ex2_approx(fmaf(__uint_as_float(s[4 * i + 0]), c2, -Lq.x));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(s[4 * i + 1]), c2, -Lq.y));
+            const float p2 = ex2_approx(fmaf(__uint_as_float(s[4 * i + 2]), c2, -Lq.z));
+            const float p3 = ex2_approx(fmaf(__uint_as_float(s[4 * i + 3]), c2, -Lq.w));
+            pw[2 * i] = pack_bf16x2(p0, p1);
+            pw[2 * i + 1] = pack_bf16x2(p2, p3);
+            dw[2 * i] = pack_bf16x2(p0 * (__uint_as_float(dp[4 * i + 0]) - Dq.x), p1 * (__uint_as_float(dp[4 * i + 1]) - Dq.y));
+            dw[2 * i + 1] = pack_bf16x2(p2 * (__uint_as_float(dp[4 * i + 2]) - Dq.z), p3 * (__uint_as_float(dp[4 * i + 3]) - Dq.w));
+          }
+          tmem_st_32x32b_x16(lane_addr + buf * 64 + half * 32, pw);
+          tmem_st_32x32b_x16(lane_addr + BL_COL_DP + buf * 64 + half * 32, dw);
+          // dS^T row -> staging tile of this query tile (chunk = 64-query block), zero for key rows past N so that the
+          // dQ product never sees a non-finite value against the zero-filled K rows
+          const uint32_t dst = stage_row + (tile & 1) * BL_STAGE_BYTES + (j & 1) * 16384;
+#pragma unroll
+          for (int pc = 0; pc < 4; ++pc) {
+            const uint32_t a = dst + (((half * 4 + pc) ^ sw) << 4);
+            if (row_valid) bl_st_shared_v4(a, dw[4 * pc], dw[4 * pc + 1], dw[4 * pc + 2], dw[4 * pc + 3]);
+            else bl_st_shared_v4(a, 0u, 0u, 0u, 0u);
+          }
+          tmem_st_wait();
+          fence_proxy_async();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_p[buf]);
+        if (threadIdx.x == 0) BL_STAMP(3 * j + 2);
+      }
+      if (lane == 0) mbar_arrive(&ld_empty[sb]);  // this warp no longer reads the item's logsumexp / delta
+      g0 += J;
+      tiles0 += nqt;
+    }
+  } else {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(BL_REGS_OTHER));
   if (warp == 13) {
     if (elect_one()) {
       // ------------------------------------------------------------------------------------ TMA producer
@@ -286,79 +362,6 @@ attn_bwd_long_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       }
     }
     __syncwarp();
-  } else if (warp < 8) {
-    // -------------------------------------------------------------------------------------- compute warps
-    const int quad = warp & 3, half = warp >> 2;
-    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
-    const float c2 = scale * BL_LOG2E;
-    const int r = quad * 32 + lane;  // key row within the 128-row tile
-    const uint32_t stage_row = smem_u32(sStage) + r * 128;
-    const int sw = r & 7;
-    const uint32_t aL = smem_u32(sL), aD = smem_u32(sD);
-    uint32_t ph_s = 0;  // bit b = parity of the next completion of bar_s[b]
-    int g0 = 0, tiles0 = 0;
-    for (int it = 0; it < num_its; ++it) {
-      const int kt = it % nkt;
-      const int sb = it & 1;
-      const uint32_t aLi = aL + sb * BL_NQ_MAX * 4, aDi = aD + sb * BL_NQ_MAX * 4;
-      mbar_wait(&ld_full[sb], (it >> 1) & 1);
-      const bool quad_active = kt * 128 + quad * 32 < N;
-      const bool row_valid = kt * 128 + r < N;
-      for (int j = 0; j < J; ++j) {
-        const int buf = (g0 + j) & 1;
-        const int w = j == J - 1 ? w_last : 64;
-        const int tile = tiles0 + (j >> 1);
-        if (threadIdx.x == 0) BL_STAMP(3 * j);
-        mbar_wait(&bar_s[buf], (ph_s >> buf) & 1);
-        if (threadIdx.x == 0) BL_STAMP(3 * j + 1);
-        ph_s ^= 1u << buf;
-        tc_fence_after();
-#ifdef TIC_EXP_NO_ELEMENTWISE  // development experiment: the tensor / barrier chain alone (results are garbage)
-        if (false) {
-#else
-        if (quad_active && half * 32 < w) {
-#endif
-          uint32_t s[32], dp[32];
-          tmem_ld_32x32b_x32(lane_addr + buf * 64 + half * 32, s);
-          tmem_ld_32x32b_x32(lane_addr + BL_COL_DP + buf * 64 + half * 32, dp);
-          tmem_ld_wait();
-          const uint32_t L4 = aLi + (j * 64 + half * 32) * 4, D4 = aDi + (j * 64 + half * 32) * 4;
-          uint32_t pw[16], dw[16];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float4 Lq = bl_ld_shared_f4(L4 + 16 * i), Dq = bl_ld_shared_f4(D4 + 16 * i);
-            const float p0 = ex2_approx(fmaf(__uint_as_float(s[4 * i + 0]), c2, -Lq.x));
-            const float p1 = ex2_approx(fmaf(__uint_as_float(s[4 * i + 1]), c2, -Lq.y));
-            const float p2 = ex2_approx(fmaf(__uint_as_float(s[4 * i + 2]), c2, -Lq.z));
-            const float p3 = ex2_approx(fmaf(__uint_as_float(s[4 * i + 3]), c2, -Lq.w));
-            pw[2 * i] = pack_bf16x2(p0, p1);
-            pw[2 * i + 1] = pack_bf16x2(p2, p3);
-            dw[2 * i] = pack_bf16x2(p0 * (__uint_as_float(dp[4 * i + 0]) - Dq.x), p1 * (__uint_as_float(dp[4 * i + 1]) - Dq.y));
-            dw[2 * i + 1] = pack_bf16x2(p2 * (__uint_as_float(dp[4 * i + 2]) - Dq.z), p3 * (__uint_as_float(dp[4 * i + 3]) - Dq.w));
-          }
-          tmem_st_32x32b_x16(lane_addr + buf * 64 + half * 32, pw);
-          tmem_st_32x32b_x16(lane_addr + BL_COL_DP + buf * 64 + half * 32, dw);
-          // dS^T row -> staging tile of this query tile (chunk = 64-query block), zero for key rows past N so that the
-          // dQ product never sees a non-finite value against the zero-filled K rows
-          const uint32_t dst = stage_row + (tile & 1) * BL_STAGE_BYTES + (j & 1) * 16384;
-#pragma unroll
-          for (int pc = 0; pc < 4; ++pc) {
-            const uint32_t a = dst + (((half * 4 + pc) ^ sw) << 4);
-            if (row_valid) bl_st_shared_v4(a, dw[4 * pc], dw[4 * pc + 1], dw[4 * pc + 2], dw[4 * pc + 3]);
-            else bl_st_shared_v4(a, 0u, 0u, 0u, 0u);
-          }
-          tmem_st_wait();
-          fence_proxy_async();
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bar_p[buf]);
-        if (threadIdx.x == 0) BL_STAMP(3 * j + 2);
-      }
-      if (lane == 0) mbar_arrive(&ld_empty[sb]);  // this warp no longer reads the item's logsumexp / delta
-      g0 += J;
-      tiles0 += nqt;
-    }
   } else if (warp < 13) {
     // -------------------------------------------------------------------------------------- drain warps
     const int quad = warp & 3;  // warps 9, 10, 11, 12 -> TMEM lane quadrants 1, 2, 3, 0
@@ -541,6 +544,7 @@ attn_bwd_long_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     }
     if (lane == 0) tma_store_wait_read<0>();  // the staging tiles must outlive the last TMA stores
   }
+  }  // roles other than the compute warps
   tc_fence_before();
   __syncthreads();
   tc_fence_after();

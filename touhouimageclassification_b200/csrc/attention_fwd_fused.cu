@@ -33,9 +33,9 @@ constexpr int FF_DRAIN_WARPS = 4;
 constexpr int FF_ISSUE_WARP = FF_ENGINE_WARPS + FF_DRAIN_WARPS;
 constexpr int FF_THREADS = 512;                             // 13 working warps + 3 idle (warps are allocated in fours)
 // Register budget: compiled for 128 registers per thread, re-balanced at run time (setmaxnreg): the two engine
-// warpgroups grow to 168 (a thread keeps its 112 scores in registers), the drain / issue warpgroups shrink to 88 --
-// 8 x 32 x (168 + 88) = the whole register file.
-constexpr int FF_REGS_ENGINE = 160, FF_REGS_OTHER = 96;
+// warpgroups grow to 152 (a thread keeps its 112 scores in registers), the drain / issue warpgroups shrink to 104 --
+// 8 x 32 x (152 + 104) = the whole register file.
+constexpr int FF_REGS_ENGINE = 152, FF_REGS_OTHER = 104;
 constexpr int FF_HD = 64;
 constexpr int FF_KV = 224;                                  // key rows staged per item
 constexpr int FF_Q_BYTES = 256 * 128;                       // 32 KB
@@ -131,69 +131,11 @@ attn_fwd_fused_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();  // the set-up above is independent of the preceding kernel; its outputs are read (and buffers written) below
-  if (warp < FF_ENGINE_WARPS) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(FF_REGS_ENGINE));
-  else asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(FF_REGS_OTHER));
   auto par = [](int u) -> uint32_t { return static_cast<uint32_t>(u >> 1) & 1u; };  // phase parity of unit u's barriers
 
-  if (warp == FF_ISSUE_WARP) {
-    if (elect_one()) {
-      // ------------------------------------------------------------------------------ TMA + MMA issue thread
-      const uint32_t idesc_s = make_idesc_bf16(128, nk, false, false);
-      constexpr uint32_t idesc_o = make_idesc_bf16(128, FF_HD, false, true);
-      auto issue_loads = [&](int item, int stage) {
-        const int h = item % H, b = item / H;
-        uint8_t* st = smem + stage * FF_STAGE_BYTES;
-        mbar_arrive_expect_tx(&bar_ld[stage], FF_STAGE_BYTES);
-        tma_load_3d(st + FF_Q_BYTES, &tm_k, &bar_ld[stage], h * FF_HD, 0, b);
-        tma_load_3d(st, &tm_q, &bar_ld[stage], h * FF_HD, 0, b);
-        tma_load_3d(st + FF_Q_BYTES + FF_KV_BYTES, &tm_v, &bar_ld[stage], h * FF_HD, 0, b);
-      };
-      // P V of unit u: P from the head of TMEM buffer u & 1, V from operand stage `stage`, O into the buffer's tail
-      auto issue_pv = [&](int u, int stage) {
-        const int b = u & 1;
-        mbar_wait(&bar_p[b], par(u));
-        tc_fence_after();
-        FF_STAMP(u, 1);
-        const uint64_t dv = make_smem_desc_sw128(smem_u32(smem + stage * FF_STAGE_BYTES) + FF_Q_BYTES + FF_KV_BYTES, 8192, 1024);
-        for (int k = 0; k < n16; ++k)
-          umma_bf16_ts(tmem_base + b * 256 + FF_O_COL, tmem_base + b * 256 + 8 * k, dv + 128 * k, idesc_o, k > 0 ? 1u : 0u);
-        umma_commit(&bar_o[b]);
-      };
-      issue_loads(blockIdx.x, 0);
-      int u = 0;
-      int prev_stage = 0;
-      for (int it = 0, item = blockIdx.x; item < num_items; ++it, item += gridDim.x) {
-        const int stage = it & 1;
-        const uint32_t aQ = smem_u32(smem + stage * FF_STAGE_BYTES), aK = aQ + FF_Q_BYTES;
-        const uint64_t dk = make_smem_desc_sw128(aK, 0, 1024);
-        const bool has_next = item + static_cast<int>(gridDim.x) < num_items;
-        for (int t = 0; t < nqt; ++t, ++u) {
-          const int b = u & 1;
-          // buffer b is free for S(u) once O(u-2) has been drained out of its tail (P V(u-2) then has completed too)
-          if (u >= 2) mbar_wait(&bar_ofree[b], par(u - 2));
-          if (t == 0) mbar_wait(&bar_ld[stage], (it >> 1) & 1);
-          tc_fence_after();
-          const uint64_t dq = make_smem_desc_sw128(aQ + t * 16384, 0, 1024);
-#pragma unroll
-          for (int k = 0; k < FF_HD / 16; ++k) umma_bf16_ss(tmem_base + b * 256, dq + 2 * k, dk + 2 * k, idesc_s, k > 0 ? 1u : 0u);
-          umma_commit(&bar_s[b]);
-          FF_STAMP(u, 0);
-          // Prefetch the next item into the other operand stage once every MMA that read it has completed. Two tiles
-          // per item: those are units u-3 and u-2, and the drain of unit u-2 was awaited above. One tile per item: the
-          // reader is unit u-1, whose P V is only issued below -- prefetch after it has completed.
-          if (nqt == 2 && t == 1 && has_next) issue_loads(item + gridDim.x, stage ^ 1);
-          if (u >= 1) issue_pv(u - 1, t == 0 ? prev_stage : stage);
-          if (nqt == 1 && has_next) {
-            if (u >= 1) mbar_wait(&bar_o[b ^ 1], par(u - 1));
-            issue_loads(item + gridDim.x, stage ^ 1);
-          }
-        }
-        prev_stage = stage;
-      }
-      if (u >= 1) issue_pv(u - 1, prev_stage);
-    }
-    __syncwarp();
-  } else if (warp < FF_ENGINE_WARPS) {
+  // setmaxnreg sits INSIDE each side of the role dispatch: ptxas budgets registers for the code a setmaxnreg dominates
+  if (warp < FF_ENGINE_WARPS) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(FF_REGS_ENGINE));
     // ---------------------------------------------------------------------------------- softmax engine
     const int quad = warp & 3;
     const float c2 = scale * FF_LOG2E;
@@ -287,6 +229,66 @@ attn_fwd_fused_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     };
     if (warp < 4) engine(std::integral_constant<int, 0>{});
     else engine(std::integral_constant<int, 1>{});
+  } else {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(FF_REGS_OTHER));
+  if (warp == FF_ISSUE_WARP) {
+    if (elect_one()) {
+      // ------------------------------------------------------------------------------ TMA + MMA issue thread
+      const uint32_t idesc_s = make_idesc_bf16(128, nk, false, false);
+      constexpr uint32_t idesc_o = make_idesc_bf16(128, FF_HD, false, true);
+      auto issue_loads = [&](int item, int stage) {
+        const int h = item % H, b = item / H;
+        uint8_t* st = smem + stage * FF_STAGE_BYTES;
+        mbar_arrive_expect_tx(&bar_ld[stage], FF_STAGE_BYTES);
+        tma_load_3d(st + FF_Q_BYTES, &tm_k, &bar_ld[stage], h * FF_HD, 0, b);
+        tma_load_3d(st, &tm_q, &bar_ld[stage], h * FF_HD, 0, b);
+        tma_load_3d(st + FF_Q_BYTES + FF_KV_BYTES, &tm_v, &bar_ld[stage], h * FF_HD, 0, b);
+      };
+      // P V of unit u: P from the head of TMEM buffer u & 1, V from operand stage `stage`, O into the buffer's tail
+      auto issue_pv = [&](int u, int stage) {
+        const int b = u & 1;
+        mbar_wait(&bar_p[b], par(u));
+        tc_fence_after();
+        FF_STAMP(u, 1);
+        const uint64_t dv = make_smem_desc_sw128(smem_u32(smem + stage * FF_STAGE_BYTES) + FF_Q_BYTES + FF_KV_BYTES, 8192, 1024);
+        for (int k = 0; k < n16; ++k)
+          umma_bf16_ts(tmem_base + b * 256 + FF_O_COL, tmem_base + b * 256 + 8 * k, dv + 128 * k, idesc_o, k > 0 ? 1u : 0u);
+        umma_commit(&bar_o[b]);
+      };
+      issue_loads(blockIdx.x, 0);
+      int u = 0;
+      int prev_stage = 0;
+      for (int it = 0, item = blockIdx.x; item < num_items; ++it, item += gridDim.x) {
+        const int stage = it & 1;
+        const uint32_t aQ = smem_u32(smem + stage * FF_STAGE_BYTES), aK = aQ + FF_Q_BYTES;
+        const uint64_t dk = make_smem_desc_sw128(aK, 0, 1024);
+        const bool has_next = item + static_cast<int>(gridDim.x) < num_items;
+        for (int t = 0; t < nqt; ++t, ++u) {
+          const int b = u & 1;
+          // buffer b is free for S(u) once O(u-2) has been drained out of its tail (P V(u-2) then has completed too)
+          if (u >= 2) mbar_wait(&bar_ofree[b], par(u - 2));
+          if (t == 0) mbar_wait(&bar_ld[stage], (it >> 1) & 1);
+          tc_fence_after();
+          const uint64_t dq = make_smem_desc_sw128(aQ + t * 16384, 0, 1024);
+#pragma unroll
+          for (int k = 0; k < FF_HD / 16; ++k) umma_bf16_ss(tmem_base + b * 256, dq + 2 * k, dk + 2 * k, idesc_s, k > 0 ? 1u : 0u);
+          umma_commit(&bar_s[b]);
+          FF_STAMP(u, 0);
+          // Prefetch the next item into the other operand stage once every MMA that read it has completed. Two tiles
+          // per item: those are units u-3 and u-2, and the drain of unit u-2 was awaited above. One tile per item: the
+          // reader is unit u-1, whose P V is only issued below -- prefetch after it has completed.
+          if (nqt == 2 && t == 1 && has_next) issue_loads(item + gridDim.x, stage ^ 1);
+          if (u >= 1) issue_pv(u - 1, t == 0 ? prev_stage : stage);
+          if (nqt == 1 && has_next) {
+            if (u >= 1) mbar_wait(&bar_o[b ^ 1], par(u - 1));
+            issue_loads(item + gridDim.x, stage ^ 1);
+          }
+        }
+        prev_stage = stage;
+      }
+      if (u >= 1) issue_pv(u - 1, prev_stage);
+    }
+    __syncwarp();
   } else if (warp < FF_ISSUE_WARP) {
     // ---------------------------------------------------------------------------------- drain warps
     const int quad = warp & 3;
@@ -352,6 +354,7 @@ attn_fwd_fused_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     }
     if (lane == 0) tma_store_wait_read<0>();  // the staging tile must outlive the last TMA store
   }
+  }  // roles other than the engine warps
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
