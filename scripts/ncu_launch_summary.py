@@ -23,10 +23,11 @@ def to_base(value: str, unit: str) -> float:
 
 def gemm_sources_sha():
     """Hash of the sources the GEMM kernel is compiled from: bench.py only quotes the DRAM traffic of a capture whose
-    hash equals the tree's (a changed kernel nulls the number instead of silently keeping a stale one)."""
+    hash equals the tree's (a changed kernel nulls the number instead of silently keeping a stale one). Run this script
+    on a capture BEFORE touching those sources again: the stamp is taken from the tree at summary time."""
     csrc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "touhouimageclassification_b200", "csrc")
     h = hashlib.sha256()
-    for f in ("gemm_tcgen05.cu", "tic_common.cuh", "tic_internal.cuh"):
+    for f in ("gemm_tcgen05.cu", "tic_common.cuh"):   # the device code of the GEMM (tic_internal.cuh holds prototypes only)
         with open(os.path.join(csrc, f), "rb") as fh:
             h.update(fh.read())
     return h.hexdigest()[:16]

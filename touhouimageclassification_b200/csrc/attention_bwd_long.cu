@@ -18,7 +18,8 @@
 // sums). Each slab element is only ever touched by one thread, in program order: no atomics, deterministic.
 // (The ring depth matters: a Q / dO block is reloaded when its products have completed and is needed again two blocks
 // later, so with 3 stages the block period was pinned to the TMA load latency.)
-// logsumexp and delta = rowsum(dO o O) (attention_delta) are read from global memory once per item by two loader warps.
+// logsumexp is read and delta = rowsum(dO o O) is COMPUTED (from the head's rows of O and dO) once per head by two loader
+// warps, one head ahead of the compute warps: there is no separate delta kernel on this path.
 // TMEM (512 columns): S[2] 0-127 | dP[2] 128-255 | dV 256-319 | dK 320-383 | dQp[2 query tiles in flight] 384-511.
 #include "tic_internal.cuh"
 
@@ -76,7 +77,8 @@ attn_bwd_long_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                      const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
                      const __grid_constant__ CUtensorMap tm_dq, const __grid_constant__ CUtensorMap tm_dk,
                      const __grid_constant__ CUtensorMap tm_dv, const float* __restrict__ lse,
-                     const float* __restrict__ delta, float* __restrict__ dq_scratch, float* __restrict__ bias_grad,
+                     const __nv_bfloat16* __restrict__ o_rows, long long ldo, const __nv_bfloat16* __restrict__ do_rows,
+                     long long lddo, float* __restrict__ dq_scratch, float* __restrict__ bias_grad,
                      int bias_mask, int N, int Nq, int H, int num_heads, float scale, long long* __restrict__ trace) {
   // trace (development builds with -DTIC_ATTN_TRACE only, else NULL): clock64 stamps of CTA 0, item 3
 #ifdef TIC_ATTN_TRACE
@@ -168,10 +170,10 @@ attn_bwd_long_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     uint32_t ph_s = 0;  // bit b = parity of the next completion of bar_s[b]
     int g0 = 0, tiles0 = 0;
     for (int it = 0; it < num_its; ++it) {
-      const int kt = it % nkt;
-      const int sb = it & 1;
+      const int kt = it % nkt, hd = it / nkt;
+      const int sb = hd & 1;   // the statistics (logsumexp, delta) belong to the head: loaded once, used by its nkt items
       const uint32_t aLi = aL + sb * BL_NQ_MAX * 4, aDi = aD + sb * BL_NQ_MAX * 4;
-      mbar_wait(&ld_full[sb], (it >> 1) & 1);
+      if (kt == 0) mbar_wait(&ld_full[sb], (hd >> 1) & 1);
       const bool quad_active = kt * 128 + quad * 32 < N;
       const bool row_valid = kt * 128 + r < N;
       for (int j = 0; j < J; ++j) {
@@ -225,7 +227,7 @@ attn_bwd_long_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         if (lane == 0) mbar_arrive(&bar_p[buf]);
         if (threadIdx.x == 0) BL_STAMP(3 * j + 2);
       }
-      if (lane == 0) mbar_arrive(&ld_empty[sb]);  // this warp no longer reads the item's logsumexp / delta
+      if (kt == nkt - 1 && lane == 0) mbar_arrive(&ld_empty[sb]);  // this warp no longer reads the head's logsumexp / delta
       g0 += J;
       tiles0 += nqt;
     }
@@ -258,18 +260,45 @@ attn_bwd_long_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     __syncwarp();
   } else if (warp >= 14) {
     // -------------------------------------------------------------------------------------- statistics loaders
-    // logsumexp (log2 domain) and delta of the item's queries -> shared memory, one item ahead of the compute warps
+    // Per head, one head ahead of the compute warps: logsumexp (log2 domain) from global memory and
+    // delta[q] = sum_d dO[q, d] * O[q, d], computed here from the head's rows of O and dO (eight lanes per 128-byte row,
+    // four rows in flight per lane group) -- no separate delta kernel, no delta round trip through HBM.
     const int t = threadIdx.x - 14 * 32;  // 0..63
-    for (int it = 0; it < num_its; ++it) {
-      const int bh = static_cast<int>(blockIdx.x) + (it / nkt) * static_cast<int>(gridDim.x);
-      const int sb = it & 1;
-      mbar_wait(&ld_empty[sb], ((it >> 1) & 1) ^ 1);
+    const int grp = t >> 3, sub = t & 7;  // 8 row groups x 8 lanes
+    const int num_hd = num_its / nkt;
+    for (int hd = 0; hd < num_hd; ++hd) {
+      const int bh = static_cast<int>(blockIdx.x) + hd * static_cast<int>(gridDim.x);
+      const int h = bh % H, b = bh / H;
+      const int sb = hd & 1;
+      mbar_wait(&ld_empty[sb], ((hd >> 1) & 1) ^ 1);
       const float* lrow = lse + static_cast<long long>(bh) * Nq;
-      const float* drow = delta + static_cast<long long>(bh) * Nq;
-      for (int qi = t; qi < J * 64; qi += 64) {
-        const bool ok = qi < Nq;
-        sL[sb * BL_NQ_MAX + qi] = ok ? __ldg(lrow + qi) * BL_LOG2E : INFINITY;  // exp2(-inf) = 0 for padded queries
-        sD[sb * BL_NQ_MAX + qi] = ok ? __ldg(drow + qi) : 0.f;
+      for (int qi = t; qi < J * 64; qi += 64)
+        sL[sb * BL_NQ_MAX + qi] = qi < Nq ? __ldg(lrow + qi) * BL_LOG2E : INFINITY;  // exp2(-inf) = 0 for padded queries
+      const __nv_bfloat16* obase = o_rows + static_cast<long long>(b) * N * ldo + h * BL_HD + sub * 8;
+      const __nv_bfloat16* gbase = do_rows + static_cast<long long>(b) * N * lddo + h * BL_HD + sub * 8;
+      for (int base = 0; base < J * 64; base += 32) {
+        uint4 ov[4], gv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int row = base + 8 * u + grp;
+          ov[u] = gv[u] = make_uint4(0u, 0u, 0u, 0u);
+          if (row < Nq) {
+            ov[u] = __ldg(reinterpret_cast<const uint4*>(obase + static_cast<long long>(row) * ldo));
+            gv[u] = __ldg(reinterpret_cast<const uint4*>(gbase + static_cast<long long>(row) * lddo));
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          float d0 = bf16_lo(ov[u].x) * bf16_lo(gv[u].x), d1 = bf16_hi(ov[u].x) * bf16_hi(gv[u].x);
+          d0 = fmaf(bf16_lo(ov[u].y), bf16_lo(gv[u].y), d0); d1 = fmaf(bf16_hi(ov[u].y), bf16_hi(gv[u].y), d1);
+          d0 = fmaf(bf16_lo(ov[u].z), bf16_lo(gv[u].z), d0); d1 = fmaf(bf16_hi(ov[u].z), bf16_hi(gv[u].z), d1);
+          d0 = fmaf(bf16_lo(ov[u].w), bf16_lo(gv[u].w), d0); d1 = fmaf(bf16_hi(ov[u].w), bf16_hi(gv[u].w), d1);
+          float d = d0 + d1;
+          d += __shfl_xor_sync(0xffffffffu, d, 1);
+          d += __shfl_xor_sync(0xffffffffu, d, 2);
+          d += __shfl_xor_sync(0xffffffffu, d, 4);
+          if (sub == 0) sD[sb * BL_NQ_MAX + base + 8 * u + grp] = d;   // rows past Nq: exact zeros
+        }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&ld_full[sb]);  // release semantics order the warp's stores before the arrival
@@ -561,12 +590,13 @@ long long attention_bwd_scratch_floats(int B, int N, int H) {
   return delta + static_cast<long long>(device_sm_count()) * BL_NQ_MAX * BL_HD;
 }
 
-// q/k/v: [B*N, ...] pitch ld, head h at column h*64; dout: [B*N, H*64] pitch lddo; dq/dk/dv pitch ldg. dq_scratch: fp32,
+// q/k/v: [B*N, ...] pitch ld, head h at column h*64; o / dout: [B*N, H*64] pitch ldo / lddo; dq/dk/dv pitch ldg. dq_scratch: fp32,
 // (SM count) x BL_NQ_MAX x 64. Only the first Nq tokens of every image are queries.
 // bias_grad (optional): fp32 [3*H*64] = q | k | v, ACCUMULATES the column sums of dq (bit 0) / dk (bit 1) / dv (bit 2).
-int attention_bwd_long(const void* q, const void* k, const void* v, long long ld, const void* dout, long long lddo,
-                       const float* lse, const float* delta, float* dq_scratch, void* dq, void* dk, void* dv, long long ldg,
-                       float* bias_grad, int bias_mask, int B, int N, int Nq, int H, float scale, cudaStream_t stream) {
+int attention_bwd_long(const void* q, const void* k, const void* v, long long ld, const void* o, long long ldo,
+                       const void* dout, long long lddo, const float* lse, float* dq_scratch, void* dq, void* dk, void* dv,
+                       long long ldg, float* bias_grad, int bias_mask, int B, int N, int Nq, int H, float scale,
+                       cudaStream_t stream) {
   if (Nq <= 0 || Nq > N) return set_error(kErrInvalidArg, "attention_bwd_long: Nq=%d must be in [1, N=%d]", Nq, N);
   if (Nq > BL_NQ_MAX) return set_error(kErrUnsupported, "attention_bwd_long: Nq=%d > %d", Nq, BL_NQ_MAX);
   CUtensorMap tq, tk, tv, tdo, tdq, tdk, tdv;
@@ -596,7 +626,8 @@ int attention_bwd_long(const void* q, const void* k, const void* v, long long ld
   cudaMallocManaged(&trace, 128 * sizeof(long long));
   for (int i = 0; i < 128; ++i) trace[i] = 0;
 #endif
-  launch_pdl(attn_bwd_long_kernel, grid, dim3(BL_THREADS), BL_SMEM, stream, tq, tk, tv, tdo, tdq, tdk, tdv, lse, delta, dq_scratch,
+  launch_pdl(attn_bwd_long_kernel, grid, dim3(BL_THREADS), BL_SMEM, stream, tq, tk, tv, tdo, tdq, tdk, tdv, lse,
+             reinterpret_cast<const __nv_bfloat16*>(o), ldo, reinterpret_cast<const __nv_bfloat16*>(dout), lddo, dq_scratch,
              bias_grad, bias_mask, N, Nq, H, heads, scale, trace);
 #ifdef TIC_ATTN_TRACE
   cudaDeviceSynchronize();

@@ -549,21 +549,21 @@ int attention_bwd_tc(const void* q, const void* k, const void* v, long long ld, 
     return attention_bwd_fused(q, k, v, ld, o, ldo, dout, lddo, lse, dq, dk, dv, lddqkv, bias_grad, bias_mask, B, N, Nq, H, scale, stream);
   }
   int rc;
+  static const bool split_kernels = std::getenv("TIC_ATTN_SPLIT") != nullptr;  // development A/B: the first-generation kernels
+  if (!split_kernels && N <= attention_bwd_long_max_queries()) {
+    // one fused kernel (delta included: its loader warps compute it per head from O and dO); dQ is accumulated over the key
+    // tiles in per-CTA fp32 slabs that sit behind the delta area of the scratch buffer (attention_bwd_scratch_floats)
+    const long long delta_floats = (static_cast<long long>(B) * H * N + 63) / 64 * 64;
+    ProfScope prof("attention_bwd", 10.0 * B * H * static_cast<double>(N) * N * AT_HD,
+                   2.0 * B * H * AT_HD * (4.0 * N + 5.0 * Nq), stream);
+    return attention_bwd_long(q, k, v, ld, o, ldo, dout, lddo, lse, delta + delta_floats, dq, dk, dv, lddqkv, bias_grad,
+                              bias_mask, B, N, Nq, H, scale, stream);
+  }
   {
     ProfScope prof("attention_delta", 0.0, 4.0 * B * static_cast<double>(Nq) * H * AT_HD, stream);
     rc = attention_delta(o, ldo, dout, lddo, delta, B, N, H, stream, Nq);
   }
   if (rc) return rc;
-  static const bool split_kernels = std::getenv("TIC_ATTN_SPLIT") != nullptr;  // development A/B: the first-generation kernels
-  if (!split_kernels && N <= attention_bwd_long_max_queries()) {
-    // one fused kernel; dQ is accumulated over the key tiles in per-CTA fp32 slabs that sit behind delta in the scratch
-    // buffer (attention_bwd_scratch_floats)
-    const long long delta_floats = (static_cast<long long>(B) * H * N + 63) / 64 * 64;
-    ProfScope prof("attention_bwd", 10.0 * B * H * static_cast<double>(N) * N * AT_HD,
-                   2.0 * B * H * AT_HD * (4.0 * N + 3.0 * Nq), stream);
-    return attention_bwd_long(q, k, v, ld, dout, lddo, lse, delta, delta + delta_floats, dq, dk, dv, lddqkv, bias_grad, bias_mask,
-                              B, N, Nq, H, scale, stream);
-  }
   ProfScope prof("attention_bwd", 10.0 * B * H * static_cast<double>(N) * N * AT_HD, 16.0 * B * H * static_cast<double>(N) * AT_HD, stream);
   // dQ: rows = queries (Q, dO), columns = keys (K, V)
   rc = launch_bwd<false>(q, dout, ld, lddo, k, v, ld, ld, lse, delta, dq, nullptr, lddqkv, B, N, Nq, H, scale, stream);

@@ -136,9 +136,10 @@ int attention_fwd_long(const void* q, const void* k, const void* v, long long ld
 // dK / dV complete per tile, dQ accumulated over the tiles in a private fp32 slab per CTA (dq_scratch, L2-resident).
 long long attention_bwd_scratch_floats(int B, int N, int H);
 int attention_bwd_long_max_queries();
-int attention_bwd_long(const void* q, const void* k, const void* v, long long ld, const void* dout, long long lddo,
-                       const float* lse, const float* delta, float* dq_scratch, void* dq, void* dk, void* dv, long long ldg,
-                       float* bias_grad, int bias_mask, int B, int N, int Nq, int H, float scale, cudaStream_t stream);
+int attention_bwd_long(const void* q, const void* k, const void* v, long long ld, const void* o, long long ldo,
+                       const void* dout, long long lddo, const float* lse, float* dq_scratch, void* dq, void* dk, void* dv,
+                       long long ldg, float* bias_grad, int bias_mask, int B, int N, int Nq, int H, float scale,
+                       cudaStream_t stream);
 // attention_bwd_fused.cu
 int attention_bwd_fused(const void* q, const void* k, const void* v, long long ld, const void* o, long long ldo,
                         const void* dout, long long lddo, const float* lse, void* dq, void* dk, void* dv, long long ldg,
