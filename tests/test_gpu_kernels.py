@@ -98,8 +98,8 @@ def test_gemm_fused_epilogues():
     assert rel(cs, out.float().sum(0)) < 1e-4
 
 
-@pytest.mark.parametrize("M,N,K", [(197, 1024, 1024), (197, 3072, 1024), (1576, 1024, 4096), (1576, 4096, 1024), (8, 1024, 1024),
-                                   (130, 136, 72), (20000, 1024, 256)])
+@pytest.mark.parametrize("M,N,K", [(197, 1024, 1024), (197, 3072, 1024), (197, 1024, 4096), (394, 4096, 1024), (1576, 1024, 4096),
+                                   (1576, 4096, 1024), (8, 1024, 1024), (130, 136, 72), (20000, 1024, 256)])
 def test_gemm_forward_epilogues_small_and_wide_tiles(M, N, K):
     """The forward epilogues pick between two tile configurations by problem size (CTA pairs with 256 x 256 tiles, or
     single CTAs with 128 x 128 tiles when the wide tiles would leave most of the machine idle: small-batch inference).
@@ -117,6 +117,10 @@ def test_gemm_forward_epilogues_small_and_wide_tiles(M, N, K):
     res = torch.randn(M, N, device=dev, generator=g)
     out = ops.gemm_bf16(a, b, bias=bias, aux=res, epilogue=ops.EPI_F32_RESID)
     assert rel(out, pre.bfloat16().float() + res) < 1e-3
+    # run to run, bit for bit
+    assert torch.equal(ops.gemm_bf16(a, b, bias=bias, aux=res, epilogue=ops.EPI_F32_RESID), out)
+    act2, _ = ops.gemm_bf16(a, b, bias=bias, epilogue=ops.EPI_BF16_GELU)
+    assert torch.equal(act2, act)
 
 
 def test_gemm_rejects_bad_arguments():

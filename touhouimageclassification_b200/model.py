@@ -491,15 +491,20 @@ class ViTForImageClassification(nn.Module):
                     c_int(bucket), c_void_p(ws.data_ptr()), c_i64(ws.numel()),
                     c_int(0), c_void_p(out.data_ptr()), _stream(dev)))
 
-            launch()  # eager warm-up: one-time function attributes and driver entry points are set outside the capture
-            torch.cuda.current_stream(dev).synchronize()
-            graph = torch.cuda.CUDAGraph()
-            # thread_local: another thread of the process (a DataLoader pin-memory thread, a second replica) may call
-            # cudaHostAlloc / cudaMalloc while this one captures; the default 'global' mode would fail the capture
             # an explicit capture stream ON THIS DEVICE: torch.cuda.graph's default one is a class-level singleton created
             # on whichever device captured first, so a replica on another GPU would capture an empty graph
             if self._capture_stream is None or self._capture_stream.device != dev:
                 self._capture_stream = torch.cuda.Stream(device=dev)
+            # eager warm-up ON THE CAPTURE STREAM: one-time function attributes, driver entry points and anything else the
+            # launchers set up per device / stream on first use happen outside the capture
+            cur = torch.cuda.current_stream(dev)
+            self._capture_stream.wait_stream(cur)
+            with torch.cuda.stream(self._capture_stream):
+                launch()
+            self._capture_stream.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            # thread_local: another thread of the process (a DataLoader pin-memory thread, a second replica) may call
+            # cudaHostAlloc / cudaMalloc while this one captures; the default 'global' mode would fail the capture
             with torch.cuda.graph(graph, stream=self._capture_stream, capture_error_mode="thread_local"):
                 launch()
             entry = dict(graph=graph, x=xin, out=out, ws=ws, shadow_ptr=self._shadow.data_ptr(),
