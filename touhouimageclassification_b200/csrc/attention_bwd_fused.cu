@@ -30,13 +30,15 @@ namespace {
 
 constexpr int FB_THREADS = 512;  // 8 compute warps + 1 TMA / MMA warp + 4 drain warps (one per TMEM lane quadrant) + 3 idle
 // Register budget: warps are allocated in groups of four, so 13 warps cost 16 x 32 x regs. The kernel is compiled for
-// 128 registers per thread and re-balances at run time (setmaxnreg): the two compute warpgroups grow to 168, the MMA /
-// drain warpgroups shrink to 88 -- 8 x 32 x (168 + 88) = the whole register file (the two sides must balance: asking for
-// more than the shrinking warps release blocks forever). Sixteen compute warps (16 query columns each, 88 registers)
+// 128 registers per thread and re-balances at run time (setmaxnreg): the two compute warpgroups grow to 152, the MMA /
+// drain warpgroups shrink to 104 -- 8 x 32 x (152 + 104) = the whole register file (the two sides must balance: asking for
+// more than the shrinking warps release blocks forever). The split is chosen by what ptxas then spills: 168 / 88 left 36
+// bytes of spills in the MMA thread's per-block issue loop (on the critical P -> MMA path), 152 / 104 leaves 8; same-box
+// A/B 0.314 -> 0.310 ms. Sixteen compute warps (16 query columns each, 88 registers)
 // measured slower, 0.312 vs 0.297 ms: the block period is set by the score -> P -> dV/dK -> next-score dependency
 // chain through the tensor pipe and the mbarrier hops, not by the elementwise pass. Signalling the S^T and dP^T
 // halves of a block separately (four barriers per block instead of two) also measured slower (0.319 ms).
-constexpr int FB_REGS_COMPUTE = 168, FB_REGS_OTHER = 88;
+constexpr int FB_REGS_COMPUTE = 152, FB_REGS_OTHER = 104;
 constexpr int FB_ROWS = 256;     // rows staged per operand
 constexpr int FB_HD = 64;
 constexpr float FB_LOG2E = 1.4426950408889634f;
@@ -371,7 +373,7 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       const int h = item % H, b = item / H;
       // One half tile (32 rows x 32 fp32 accumulator columns of this warp's lane quadrant): TMEM -> scaled, packed bf16
       // -> staging slot (64-byte swizzle); column sums of the bf16 rows accumulate into the QKV bias gradient when asked
-      // for. Done one half tile at a time so that the drain warps live within their 88 registers.
+      // for. Done one half tile at a time so that the drain warps live within their registers.
       auto stage_half = [&](int slot, uint32_t col, float f, bool valid, float* bias_dst, int half) {
         uint32_t rr[32];
         tmem_ld_32x32b_x32(lane_addr + col, rr);

@@ -32,7 +32,7 @@ namespace tic {
 namespace {
 
 constexpr int BL_THREADS = 512;  // 8 compute warps | MMA warp | 4 drain warps | TMA producer warp | 2 statistics loader warps
-constexpr int BL_REGS_COMPUTE = 168, BL_REGS_OTHER = 88;  // see attention_bwd_fused.cu
+constexpr int BL_REGS_COMPUTE = 160, BL_REGS_OTHER = 96;  // see attention_bwd_fused.cu
 constexpr int BL_HD = 64;
 constexpr int BL_NQ_MAX = 640;   // queries per image this kernel has logsumexp / delta slots for
 constexpr float BL_LOG2E = 1.4426950408889634f;
