@@ -33,9 +33,9 @@ constexpr int FF_DRAIN_WARPS = 4;
 constexpr int FF_ISSUE_WARP = FF_ENGINE_WARPS + FF_DRAIN_WARPS;
 constexpr int FF_THREADS = 512;                             // 13 working warps + 3 idle (warps are allocated in fours)
 // Register budget: compiled for 128 registers per thread, re-balanced at run time (setmaxnreg): the two engine
-// warpgroups grow to 152 (a thread keeps its 112 scores in registers), the drain / issue warpgroups shrink to 104 --
-// 8 x 32 x (152 + 104) = the whole register file.
-constexpr int FF_REGS_ENGINE = 152, FF_REGS_OTHER = 104;
+// warpgroups grow to 160 (a thread keeps its 112 scores in registers), the drain / issue warpgroups shrink to 96 --
+// 8 x 32 x (160 + 96) = the whole register file.
+constexpr int FF_REGS_ENGINE = 160, FF_REGS_OTHER = 96;
 constexpr int FF_HD = 64;
 constexpr int FF_KV = 224;                                  // key rows staged per item
 constexpr int FF_Q_BYTES = 256 * 128;                       // 32 KB
