@@ -72,7 +72,11 @@ ln_fwd_kernel(const float* __restrict__ x, long long ldx, const float* __restric
 // shared memory (keeps the register count low enough for 3 CTAs / SM), reduced across the CTA's warps at
 // the end, then one atomicAdd per column per CTA.
 template <int VEC>
-__global__ void __launch_bounds__(LN_WARPS * 32, 2)
+// One CTA (8 warps) per SM, whatever registers it takes (220 at D = 1024): asking for two CTAs per SM capped the kernel at
+// 128 registers and ptxas spilled 200 bytes of the row held in registers -- the kernel keeps 10 KB of loads in flight per
+// warp, so eight warps already cover the HBM latency. Same-box A/B at [50432, 1024]: 0.1755 -> 0.154 ms (4.7 -> 5.37 TB/s,
+// 0.82 of the measured copy bandwidth).
+__global__ void __launch_bounds__(LN_WARPS * 32, 1)
 ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long lddy, const float* __restrict__ x, long long ldx,
               const float* __restrict__ mean_in, const float* __restrict__ rstd_in, const float* __restrict__ gamma,
               const float* dres, long long lddres, int rows, float* dx, long long lddx,
@@ -129,8 +133,7 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long lddy, const float*
     const uint2* dyr = reinterpret_cast<const uint2*>(dy + static_cast<long long>(row) * lddy);
     const float4* rr = dres ? reinterpret_cast<const float4*>(dres + static_cast<long long>(row) * lddres) : nullptr;
     // All of the row's HBM reads (x, dy and the residual gradient) are issued up front: 10 KB in flight per warp
-    // instead of two dependent round trips. xhat and dy * gamma are recomputed in the second pass rather than kept,
-    // which holds the kernel at 2 CTAs / SM.
+    // instead of two dependent round trips. xhat and dy * gamma are recomputed in the second pass rather than kept.
     float4 xv[VEC], rv[VEC];
     uint2 dv[VEC];
 #pragma unroll
