@@ -31,6 +31,22 @@ def test_native_sampler_matches_oracle_sampler(lib):
         assert np.array_equal(np.sort(ints[:, 5:9], axis=1), np.tile(np.arange(4), (200, 1)))  # a permutation
 
 
+def test_sharded_sample_indices_tile_the_global_batch(lib):
+    """GpuAugment.shard(rank, world): rank r's batch of B in step k draws the parameters of global samples
+    k * world * B + r * B ... + B -- together the ranks reproduce the one-process stream, and no two ranks share a draw."""
+    from touhouimageclassification_b200.augment import GpuAugment, sample_params
+    B, world, seed = 6, 4, 13
+    whole, _ = sample_params(seed, 0, 3 * world * B, 256, 256, 224, "full")
+    for rank in range(world):
+        aug = GpuAugment(seed=seed).shard(rank, world)
+        for step in range(3):
+            first = aug.samples_seen + aug.rank * B            # what _prepare computes for a batch of B
+            aug.samples_seen += B * aug.world_size
+            ints, _ = sample_params(seed, first, B, 256, 256, 224, "full")
+            lo = step * world * B + rank * B
+            assert first == lo and np.array_equal(ints, whole[lo:lo + B]), (rank, step)
+
+
 def test_sampler_statistics_follow_torchvision_rules(lib):
     from touhouimageclassification_b200.augment import sample_params
     ints, floats = sample_params(11, 0, 4000, 256, 256)

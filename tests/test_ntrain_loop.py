@@ -181,3 +181,19 @@ def test_train_main_command_line_transform_path(tmp_path):
     assert os.path.exists(out) and set(inner) == set(lm.vit.state_dict())
     with pytest.raises(SystemExit, match="No checkpoint to transform"):
         ntrain.train_main(**kw, argv=["--transform", out])
+
+
+def test_data_parallel_fit_refuses_a_stock_optimizer():
+    """The gradient exchange lives in the fused step (FusedAdamW + DataParallelTrainer): with a stock optimizer every rank
+    would train on its own shard without any exchange, silently. fit() says so instead."""
+    m = Scripted([0.5])
+    train, val = loaders()
+
+    class FakeDP:
+        world_size = 2
+
+        def _grad_sync(self, *a):
+            raise AssertionError("must not be reached")
+
+    with pytest.raises(ValueError, match="FusedAdamW"):
+        ntrain.fit(m, train, val, max_epochs=1, data_parallel=FakeDP())
