@@ -18,7 +18,10 @@
 // [0, nk / 2), and the O accumulator in [192, 256) over the dead tail of S. The score MMAs of unit u+1, the P V MMAs
 // and the drain of unit u-1 all run under the engine's exp2 pass of unit u.
 // (Measured and rejected: accumulating O(u) in the tail of the OTHER buffer so that S(u+2) need not wait for the drain
-// of O(u) -- P V(u) must then wait until the engine has pulled S(u+1) into registers, which costs more than it saves.)
+// of O(u) -- P V(u) must then wait until the engine has pulled S(u+1) into registers, which costs more than it saves.
+// Also rejected: taking every 4th / 2nd exponential off the SFU with a cubic exp2 polynomial on the FMA pipe (the
+// FlashAttention-4 trick): 0.109 -> 0.142 / 0.190 ms -- nine extra instructions per element cost more issue slots than
+// the 8 SFU clocks they save.)
 // Outputs leave through shared-memory tiles and TMA stores (rows past Nq are clipped by the tensor map): direct
 // 16-byte stores at a 2 KB row pitch cost ~300 clk per instruction.
 #include "tic_internal.cuh"
