@@ -249,217 +249,217 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       }
     }
   } else {
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(FB_REGS_OTHER));
-  if (warp == 8) {
-    if (elect_one()) {  // one issuing thread on the uniform datapath (a lane == 0 test costs ~45 clk per MMA)
-      // ---------------------------------------------------------------------------------- TMA + MMA issue loop
-      constexpr uint32_t idesc_ts = make_idesc_bf16(128, FB_HD, false, true);
-      constexpr uint32_t idesc_dq = make_idesc_bf16(128, FB_HD, true, true);
-      const uint32_t aQ = smem_u32(sQ), aDO = smem_u32(sDO), aK = smem_u32(sK), aV = smem_u32(sV), aS = smem_u32(sStage);
-      auto issue_loads = [&](int item) {
-        const int h = item % H, b = item / H;
-        mbar_arrive_expect_tx(&bar_load[0], 2 * FB_OPER_BYTES);
-        tma_load_3d(sK, &tm_k, &bar_load[0], h * FB_HD, 0, b);
-        tma_load_3d(sQ, &tm_q, &bar_load[0], h * FB_HD, 0, b);
-        mbar_arrive_expect_tx(&bar_load[1], 3 * FB_OPER_BYTES);
-        tma_load_3d(sDO, &tm_do, &bar_load[1], h * FB_HD, 0, b);
-        tma_load_3d(sO, &tm_o, &bar_load[1], h * FB_HD, 0, b);
-        tma_load_3d(sV, &tm_v, &bar_load[1], h * FB_HD, 0, b);
-      };
-      uint32_t ph_p = 0, use_acc = 0, use_vk = 0;  // ph_p: bit b = parity of the next completion of bar_p[b]
-      issue_loads(blockIdx.x);
-      for (int it = 0, item = blockIdx.x; item < num_items; ++it, item += gridDim.x) {
-        // The operand buffers are single (the SM's shared memory holds one head), so the next item's loads can only be
-        // issued when this item's last MMA has completed -- but its addresses are known now: pull the five boxes into L2
-        // so that those loads pay L2 latency, not DRAM latency, on the critical path between two items.
-        if (item + static_cast<int>(gridDim.x) < num_items) {
-          const int nx = item + gridDim.x, nh = nx % H, nb = nx / H;
-          tma_prefetch_l2_3d(&tm_k, nh * FB_HD, 0, nb);
-          tma_prefetch_l2_3d(&tm_q, nh * FB_HD, 0, nb);
-          tma_prefetch_l2_3d(&tm_do, nh * FB_HD, 0, nb);
-          tma_prefetch_l2_3d(&tm_o, nh * FB_HD, 0, nb);
-          tma_prefetch_l2_3d(&tm_v, nh * FB_HD, 0, nb);
-        }
-        auto issue_scores = [&](int j) {
-          const int kt = j >= nqb ? 1 : 0, qb = j - kt * nqb, buf = j & 1;
-          const int w = qb == nqb - 1 ? w_last : 64;
-          const uint32_t idesc = make_idesc_bf16(128, w, false, false);
-          const uint64_t dK_ = make_smem_desc_sw128(aK + kt * 16384, 0, 1024), dQ_ = make_smem_desc_sw128(aQ + qb * 8192, 0, 1024);
-          const uint64_t dV_ = make_smem_desc_sw128(aV + kt * 16384, 0, 1024), dO_ = make_smem_desc_sw128(aDO + qb * 8192, 0, 1024);
-          if (j == 0) { mbar_wait(&bar_load[0], it & 1); tc_fence_after(); }
-#pragma unroll
-          for (int k = 0; k < FB_HD / 16; ++k) umma_bf16_ss(tmem_base + buf * 64, dK_ + 2 * k, dQ_ + 2 * k, idesc, k > 0 ? 1u : 0u);
-          if (j == 0) { mbar_wait(&bar_load[1], it & 1); tc_fence_after(); }
-#pragma unroll
-          for (int k = 0; k < FB_HD / 16; ++k)
-            umma_bf16_ss(tmem_base + FB_COL_DP + buf * 64, dV_ + 2 * k, dO_ + 2 * k, idesc, k > 0 ? 1u : 0u);
-          umma_commit(&bar_s[buf]);
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(FB_REGS_OTHER));
+    if (warp == 8) {
+      if (elect_one()) {  // one issuing thread on the uniform datapath (a lane == 0 test costs ~45 clk per MMA)
+        // ---------------------------------------------------------------------------------- TMA + MMA issue loop
+        constexpr uint32_t idesc_ts = make_idesc_bf16(128, FB_HD, false, true);
+        constexpr uint32_t idesc_dq = make_idesc_bf16(128, FB_HD, true, true);
+        const uint32_t aQ = smem_u32(sQ), aDO = smem_u32(sDO), aK = smem_u32(sK), aV = smem_u32(sV), aS = smem_u32(sStage);
+        auto issue_loads = [&](int item) {
+          const int h = item % H, b = item / H;
+          mbar_arrive_expect_tx(&bar_load[0], 2 * FB_OPER_BYTES);
+          tma_load_3d(sK, &tm_k, &bar_load[0], h * FB_HD, 0, b);
+          tma_load_3d(sQ, &tm_q, &bar_load[0], h * FB_HD, 0, b);
+          mbar_arrive_expect_tx(&bar_load[1], 3 * FB_OPER_BYTES);
+          tma_load_3d(sDO, &tm_do, &bar_load[1], h * FB_HD, 0, b);
+          tma_load_3d(sO, &tm_o, &bar_load[1], h * FB_HD, 0, b);
+          tma_load_3d(sV, &tm_v, &bar_load[1], h * FB_HD, 0, b);
         };
-        FB_STAMP(64);
-        issue_scores(0);
-        FB_STAMP(65);
-        if (J > 1) issue_scores(1);
-        FB_STAMP(66);
-        for (int j = 0; j < J; ++j) {
-          const int kt = j >= nqb ? 1 : 0, qb = j - kt * nqb, buf = j & 1;
-          mbar_wait(&bar_p[buf], (ph_p >> buf) & 1);
-          FB_STAMP(70 + 2 * j);
-          ph_p ^= 1u << buf;
-          tc_fence_after();
-          if (qb == 0 && (it > 0 || kt > 0)) {  // the previous key tile's dV / dK have left TMEM
-            mbar_wait(bar_free_vk, use_vk & 1);
-            ++use_vk;
+        uint32_t ph_p = 0, use_acc = 0, use_vk = 0;  // ph_p: bit b = parity of the next completion of bar_p[b]
+        issue_loads(blockIdx.x);
+        for (int it = 0, item = blockIdx.x; item < num_items; ++it, item += gridDim.x) {
+          // The operand buffers are single (the SM's shared memory holds one head), so the next item's loads can only be
+          // issued when this item's last MMA has completed -- but its addresses are known now: pull the five boxes into L2
+          // so that those loads pay L2 latency, not DRAM latency, on the critical path between two items.
+          if (item + static_cast<int>(gridDim.x) < num_items) {
+            const int nx = item + gridDim.x, nh = nx % H, nb = nx / H;
+            tma_prefetch_l2_3d(&tm_k, nh * FB_HD, 0, nb);
+            tma_prefetch_l2_3d(&tm_q, nh * FB_HD, 0, nb);
+            tma_prefetch_l2_3d(&tm_do, nh * FB_HD, 0, nb);
+            tma_prefetch_l2_3d(&tm_o, nh * FB_HD, 0, nb);
+            tma_prefetch_l2_3d(&tm_v, nh * FB_HD, 0, nb);
+          }
+          auto issue_scores = [&](int j) {
+            const int kt = j >= nqb ? 1 : 0, qb = j - kt * nqb, buf = j & 1;
+            const int w = qb == nqb - 1 ? w_last : 64;
+            const uint32_t idesc = make_idesc_bf16(128, w, false, false);
+            const uint64_t dK_ = make_smem_desc_sw128(aK + kt * 16384, 0, 1024), dQ_ = make_smem_desc_sw128(aQ + qb * 8192, 0, 1024);
+            const uint64_t dV_ = make_smem_desc_sw128(aV + kt * 16384, 0, 1024), dO_ = make_smem_desc_sw128(aDO + qb * 8192, 0, 1024);
+            if (j == 0) { mbar_wait(&bar_load[0], it & 1); tc_fence_after(); }
+#pragma unroll
+            for (int k = 0; k < FB_HD / 16; ++k) umma_bf16_ss(tmem_base + buf * 64, dK_ + 2 * k, dQ_ + 2 * k, idesc, k > 0 ? 1u : 0u);
+            if (j == 0) { mbar_wait(&bar_load[1], it & 1); tc_fence_after(); }
+#pragma unroll
+            for (int k = 0; k < FB_HD / 16; ++k)
+              umma_bf16_ss(tmem_base + FB_COL_DP + buf * 64, dV_ + 2 * k, dO_ + 2 * k, idesc, k > 0 ? 1u : 0u);
+            umma_commit(&bar_s[buf]);
+          };
+          FB_STAMP(64);
+          issue_scores(0);
+          FB_STAMP(65);
+          if (J > 1) issue_scores(1);
+          FB_STAMP(66);
+          for (int j = 0; j < J; ++j) {
+            const int kt = j >= nqb ? 1 : 0, qb = j - kt * nqb, buf = j & 1;
+            mbar_wait(&bar_p[buf], (ph_p >> buf) & 1);
+            FB_STAMP(70 + 2 * j);
+            ph_p ^= 1u << buf;
             tc_fence_after();
-          }
-          const int ksteps = (qb == nqb - 1 ? w_last : 64) >> 4;
-          const uint64_t dO_mn = make_smem_desc_sw128(aDO + qb * 8192, 8192, 1024);
-          const uint64_t dQ_mn = make_smem_desc_sw128(aQ + qb * 8192, 8192, 1024);
-          for (int k = 0; k < ksteps; ++k) {  // dV += P^T dO
-            const uint32_t a = tmem_base + buf * 64 + (k >> 1) * 32 + (k & 1) * 8;
-            umma_bf16_ts(tmem_base + FB_COL_DV, a, dO_mn + 128 * k, idesc_ts, (qb > 0 || k > 0) ? 1u : 0u);
-          }
-          for (int k = 0; k < ksteps; ++k) {  // dK += dS^T Q
-            const uint32_t a = tmem_base + FB_COL_DP + buf * 64 + (k >> 1) * 32 + (k & 1) * 8;
-            umma_bf16_ts(tmem_base + FB_COL_DK, a, dQ_mn + 128 * k, idesc_ts, (qb > 0 || k > 0) ? 1u : 0u);
-          }
-          // dV / dK of a key tile that is not the last one are complete here: let the drain warps start before the score
-          // and dQ products queued behind them
-          const bool tile_end = qb == nqb - 1, early = tile_end && kt < nkt - 1;
-          if (early) umma_commit(bar_acc);
-          // the P^T / dS^T columns of this buffer have been consumed (in issue order): refill it with the scores of
-          // block j+2 before the dQ product, which the compute warps do not wait for
-          if (j + 2 < J) issue_scores(j + 2);
-          if ((qb & 1) || qb == nqb - 1) {    // dQ[query tile] += dS K over this key tile
-            const int qt = qb >> 1;
-            if (kt == 0 && qt == 0 && it > 0) {  // the previous item's dQ has left TMEM
-              mbar_wait(bar_free_q, (it - 1) & 1);
+            if (qb == 0 && (it > 0 || kt > 0)) {  // the previous key tile's dV / dK have left TMEM
+              mbar_wait(bar_free_vk, use_vk & 1);
+              ++use_vk;
               tc_fence_after();
             }
-            const int kvalid = min(128, N - kt * 128);
-            const int ks = (kvalid + 15) >> 4;
-            // staging tile of (key tile, query tile): with at most two query blocks there is one query tile and the two key
-            // tiles alternate between the two staging tiles (a tile is never rewritten while its dQ product may be reading it)
-            const int st = nqb <= 2 ? (kt & 1) : qt;
-            const uint64_t dS_mn = make_smem_desc_sw128(aS + st * FB_STAGE_BYTES, 16384, 1024);
-            const uint64_t dK_mn = make_smem_desc_sw128(aK + kt * 16384, 8192, 1024);
-            for (int k = 0; k < ks; ++k)
-              umma_bf16_ss(tmem_base + FB_COL_DQ + qt * 64, dS_mn + 128 * k, dK_mn + 128 * k, idesc_dq, (kt > 0 || k > 0) ? 1u : 0u);
-          }
-          FB_STAMP(71 + 2 * j);
-          if (tile_end) {
-            if (!early) umma_commit(bar_acc);
-            if (kt == nkt - 1 && item + static_cast<int>(gridDim.x) < num_items) {
-              // every MMA of this item has read its operands: refill the operand buffers for the next item
-              mbar_wait(bar_acc, use_acc & 1);
-              FB_STAMP(100);
-              issue_loads(item + gridDim.x);
-              FB_STAMP(101);
+            const int ksteps = (qb == nqb - 1 ? w_last : 64) >> 4;
+            const uint64_t dO_mn = make_smem_desc_sw128(aDO + qb * 8192, 8192, 1024);
+            const uint64_t dQ_mn = make_smem_desc_sw128(aQ + qb * 8192, 8192, 1024);
+            for (int k = 0; k < ksteps; ++k) {  // dV += P^T dO
+              const uint32_t a = tmem_base + buf * 64 + (k >> 1) * 32 + (k & 1) * 8;
+              umma_bf16_ts(tmem_base + FB_COL_DV, a, dO_mn + 128 * k, idesc_ts, (qb > 0 || k > 0) ? 1u : 0u);
             }
-            ++use_acc;
+            for (int k = 0; k < ksteps; ++k) {  // dK += dS^T Q
+              const uint32_t a = tmem_base + FB_COL_DP + buf * 64 + (k >> 1) * 32 + (k & 1) * 8;
+              umma_bf16_ts(tmem_base + FB_COL_DK, a, dQ_mn + 128 * k, idesc_ts, (qb > 0 || k > 0) ? 1u : 0u);
+            }
+            // dV / dK of a key tile that is not the last one are complete here: let the drain warps start before the score
+            // and dQ products queued behind them
+            const bool tile_end = qb == nqb - 1, early = tile_end && kt < nkt - 1;
+            if (early) umma_commit(bar_acc);
+            // the P^T / dS^T columns of this buffer have been consumed (in issue order): refill it with the scores of
+            // block j+2 before the dQ product, which the compute warps do not wait for
+            if (j + 2 < J) issue_scores(j + 2);
+            if ((qb & 1) || qb == nqb - 1) {    // dQ[query tile] += dS K over this key tile
+              const int qt = qb >> 1;
+              if (kt == 0 && qt == 0 && it > 0) {  // the previous item's dQ has left TMEM
+                mbar_wait(bar_free_q, (it - 1) & 1);
+                tc_fence_after();
+              }
+              const int kvalid = min(128, N - kt * 128);
+              const int ks = (kvalid + 15) >> 4;
+              // staging tile of (key tile, query tile): with at most two query blocks there is one query tile and the two key
+              // tiles alternate between the two staging tiles (a tile is never rewritten while its dQ product may be reading it)
+              const int st = nqb <= 2 ? (kt & 1) : qt;
+              const uint64_t dS_mn = make_smem_desc_sw128(aS + st * FB_STAGE_BYTES, 16384, 1024);
+              const uint64_t dK_mn = make_smem_desc_sw128(aK + kt * 16384, 8192, 1024);
+              for (int k = 0; k < ks; ++k)
+                umma_bf16_ss(tmem_base + FB_COL_DQ + qt * 64, dS_mn + 128 * k, dK_mn + 128 * k, idesc_dq, (kt > 0 || k > 0) ? 1u : 0u);
+            }
+            FB_STAMP(71 + 2 * j);
+            if (tile_end) {
+              if (!early) umma_commit(bar_acc);
+              if (kt == nkt - 1 && item + static_cast<int>(gridDim.x) < num_items) {
+                // every MMA of this item has read its operands: refill the operand buffers for the next item
+                mbar_wait(bar_acc, use_acc & 1);
+                FB_STAMP(100);
+                issue_loads(item + gridDim.x);
+                FB_STAMP(101);
+              }
+              ++use_acc;
+            }
           }
         }
       }
+      __syncwarp();
     }
-    __syncwarp();
-  }
-  if (warp > 8 && warp < 13) {
-    // ------------------------------------------------------------------------------------ drain warps
-    const int quad = warp & 3;  // warps 9, 10, 11, 12 -> TMEM lane quadrants 1, 2, 3, 0
-    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
-    const uint32_t stage = smem_u32(sOut) + (warp - 9) * 8192;  // four 2 KB tiles: [32 rows][64 B], 64-byte swizzle
-    const int r = quad * 32 + lane;
-    uint32_t use_acc = 0;
-    for (int it = 0, item = blockIdx.x; item < num_items; ++it, item += gridDim.x) {
-      const int h = item % H, b = item / H;
-      // One half tile (32 rows x 32 fp32 accumulator columns of this warp's lane quadrant): TMEM -> scaled, packed bf16
-      // -> staging slot (64-byte swizzle); column sums of the bf16 rows accumulate into the QKV bias gradient when asked
-      // for. Done one half tile at a time so that the drain warps live within their registers.
-      auto stage_half = [&](int slot, uint32_t col, float f, bool valid, float* bias_dst, int half) {
-        uint32_t rr[32];
-        tmem_ld_32x32b_x32(lane_addr + col, rr);
-        tmem_ld_wait();
-        uint32_t pk[16];
+    if (warp > 8 && warp < 13) {
+      // ------------------------------------------------------------------------------------ drain warps
+      const int quad = warp & 3;  // warps 9, 10, 11, 12 -> TMEM lane quadrants 1, 2, 3, 0
+      const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+      const uint32_t stage = smem_u32(sOut) + (warp - 9) * 8192;  // four 2 KB tiles: [32 rows][64 B], 64-byte swizzle
+      const int r = quad * 32 + lane;
+      uint32_t use_acc = 0;
+      for (int it = 0, item = blockIdx.x; item < num_items; ++it, item += gridDim.x) {
+        const int h = item % H, b = item / H;
+        // One half tile (32 rows x 32 fp32 accumulator columns of this warp's lane quadrant): TMEM -> scaled, packed bf16
+        // -> staging slot (64-byte swizzle); column sums of the bf16 rows accumulate into the QKV bias gradient when asked
+        // for. Done one half tile at a time so that the drain warps live within their registers.
+        auto stage_half = [&](int slot, uint32_t col, float f, bool valid, float* bias_dst, int half) {
+          uint32_t rr[32];
+          tmem_ld_32x32b_x32(lane_addr + col, rr);
+          tmem_ld_wait();
+          uint32_t pk[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(__uint_as_float(rr[2 * i]) * f, __uint_as_float(rr[2 * i + 1]) * f);
-        const uint32_t base = stage + slot * 2048 + lane * 64;
-        const int x = (lane >> 1) & 3;
+          for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(__uint_as_float(rr[2 * i]) * f, __uint_as_float(rr[2 * i + 1]) * f);
+          const uint32_t base = stage + slot * 2048 + lane * 64;
+          const int x = (lane >> 1) & 3;
 #pragma unroll
-        for (int pc = 0; pc < 4; ++pc)
-          st_shared_v4(base + ((pc ^ x) << 4), pk[4 * pc], pk[4 * pc + 1], pk[4 * pc + 2], pk[4 * pc + 3]);
-        if (bias_dst != nullptr) {
-          float v[32];
+          for (int pc = 0; pc < 4; ++pc)
+            st_shared_v4(base + ((pc ^ x) << 4), pk[4 * pc], pk[4 * pc + 1], pk[4 * pc + 2], pk[4 * pc + 3]);
+          if (bias_dst != nullptr) {
+            float v[32];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            v[2 * i] = valid ? bf16_lo(pk[i]) : 0.f;
-            v[2 * i + 1] = valid ? bf16_hi(pk[i]) : 0.f;
+            for (int i = 0; i < 16; ++i) {
+              v[2 * i] = valid ? bf16_lo(pk[i]) : 0.f;
+              v[2 * i + 1] = valid ? bf16_hi(pk[i]) : 0.f;
+            }
+            const float cs = warp_colsum32(v, lane);
+            atomicAdd(bias_dst + h * FB_HD + half * 32 + lane, cs);
           }
-          const float cs = warp_colsum32(v, lane);
-          atomicAdd(bias_dst + h * FB_HD + half * 32 + lane, cs);
-        }
-      };
-      for (int kt = 0; kt < nkt; ++kt) {
-        const bool quad_active = kt * 128 + quad * 32 < N;
-        const int row0 = kt * 128 + quad * 32;
-        const bool valid = kt * 128 + r < N;
-        mbar_wait(bar_acc, use_acc & 1);
-        ++use_acc;
-        tc_fence_after();
-        if (lane == 0) tma_store_wait_read<0>();  // this warp's staging slots are free again (stores issued long ago)
-        __syncwarp();
-        if (quad_active) {
-          float* vdst = (bias_mask & 4) ? bias_grad + 2 * H * FB_HD : nullptr;
-          float* kdst = (bias_mask & 2) ? bias_grad + H * FB_HD : nullptr;
-          stage_half(0, FB_COL_DV, 1.0f, valid, vdst, 0);
-          stage_half(1, FB_COL_DV + 32, 1.0f, valid, vdst, 1);
-          stage_half(2, FB_COL_DK, scale, valid, kdst, 0);
-          stage_half(3, FB_COL_DK + 32, scale, valid, kdst, 1);
-          fence_proxy_async();
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(bar_free_vk);  // the MMA thread may overwrite dV / dK
-          if (quad_active) {
-            tma_store_3d_addr(&tm_dv, stage, h * FB_HD, row0, b);
-            tma_store_3d_addr(&tm_dv, stage + 2048, h * FB_HD + 32, row0, b);
-            tma_store_3d_addr(&tm_dk, stage + 4096, h * FB_HD, row0, b);
-            tma_store_3d_addr(&tm_dk, stage + 6144, h * FB_HD + 32, row0, b);
-            tma_store_commit();
-          }
-        }
-        if (kt == nkt - 1) {  // dQ of both query tiles (all of this item's MMAs have completed)
-          const bool q0 = quad * 32 < Nq, q1 = 128 + quad * 32 < Nq;
-          float* qdst = (bias_mask & 1) ? bias_grad : nullptr;
-          if (lane == 0) tma_store_wait_read<0>();  // the dV / dK stores above have finished reading the slots
+        };
+        for (int kt = 0; kt < nkt; ++kt) {
+          const bool quad_active = kt * 128 + quad * 32 < N;
+          const int row0 = kt * 128 + quad * 32;
+          const bool valid = kt * 128 + r < N;
+          mbar_wait(bar_acc, use_acc & 1);
+          ++use_acc;
+          tc_fence_after();
+          if (lane == 0) tma_store_wait_read<0>();  // this warp's staging slots are free again (stores issued long ago)
           __syncwarp();
-          if (q0) {
-            stage_half(0, FB_COL_DQ, scale, r < Nq, qdst, 0);
-            stage_half(1, FB_COL_DQ + 32, scale, r < Nq, qdst, 1);
+          if (quad_active) {
+            float* vdst = (bias_mask & 4) ? bias_grad + 2 * H * FB_HD : nullptr;
+            float* kdst = (bias_mask & 2) ? bias_grad + H * FB_HD : nullptr;
+            stage_half(0, FB_COL_DV, 1.0f, valid, vdst, 0);
+            stage_half(1, FB_COL_DV + 32, 1.0f, valid, vdst, 1);
+            stage_half(2, FB_COL_DK, scale, valid, kdst, 0);
+            stage_half(3, FB_COL_DK + 32, scale, valid, kdst, 1);
+            fence_proxy_async();
           }
-          if (q1) {
-            stage_half(2, FB_COL_DQ + 64, scale, 128 + r < Nq, qdst, 0);
-            stage_half(3, FB_COL_DQ + 96, scale, 128 + r < Nq, qdst, 1);
-          }
-          if (q0) fence_proxy_async();
           tc_fence_before();
           __syncwarp();
           if (lane == 0) {
-            mbar_arrive(bar_free_q);
+            mbar_arrive(bar_free_vk);  // the MMA thread may overwrite dV / dK
+            if (quad_active) {
+              tma_store_3d_addr(&tm_dv, stage, h * FB_HD, row0, b);
+              tma_store_3d_addr(&tm_dv, stage + 2048, h * FB_HD + 32, row0, b);
+              tma_store_3d_addr(&tm_dk, stage + 4096, h * FB_HD, row0, b);
+              tma_store_3d_addr(&tm_dk, stage + 6144, h * FB_HD + 32, row0, b);
+              tma_store_commit();
+            }
+          }
+          if (kt == nkt - 1) {  // dQ of both query tiles (all of this item's MMAs have completed)
+            const bool q0 = quad * 32 < Nq, q1 = 128 + quad * 32 < Nq;
+            float* qdst = (bias_mask & 1) ? bias_grad : nullptr;
+            if (lane == 0) tma_store_wait_read<0>();  // the dV / dK stores above have finished reading the slots
+            __syncwarp();
             if (q0) {
-              tma_store_3d_addr(&tm_dq, stage, h * FB_HD, quad * 32, b);
-              tma_store_3d_addr(&tm_dq, stage + 2048, h * FB_HD + 32, quad * 32, b);
+              stage_half(0, FB_COL_DQ, scale, r < Nq, qdst, 0);
+              stage_half(1, FB_COL_DQ + 32, scale, r < Nq, qdst, 1);
             }
             if (q1) {
-              tma_store_3d_addr(&tm_dq, stage + 4096, h * FB_HD, 128 + quad * 32, b);
-              tma_store_3d_addr(&tm_dq, stage + 6144, h * FB_HD + 32, 128 + quad * 32, b);
+              stage_half(2, FB_COL_DQ + 64, scale, 128 + r < Nq, qdst, 0);
+              stage_half(3, FB_COL_DQ + 96, scale, 128 + r < Nq, qdst, 1);
             }
-            if (q0) tma_store_commit();
+            if (q0) fence_proxy_async();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              mbar_arrive(bar_free_q);
+              if (q0) {
+                tma_store_3d_addr(&tm_dq, stage, h * FB_HD, quad * 32, b);
+                tma_store_3d_addr(&tm_dq, stage + 2048, h * FB_HD + 32, quad * 32, b);
+              }
+              if (q1) {
+                tma_store_3d_addr(&tm_dq, stage + 4096, h * FB_HD, 128 + quad * 32, b);
+                tma_store_3d_addr(&tm_dq, stage + 6144, h * FB_HD + 32, 128 + quad * 32, b);
+              }
+              if (q0) tma_store_commit();
+            }
           }
         }
       }
+      if (lane == 0) tma_store_wait_read<0>();  // the staging tiles must outlive the last TMA stores
     }
-    if (lane == 0) tma_store_wait_read<0>();  // the staging tiles must outlive the last TMA stores
-  }
   }  // roles other than the compute warps
   tc_fence_before();
   __syncthreads();

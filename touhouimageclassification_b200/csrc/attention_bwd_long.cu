@@ -232,347 +232,347 @@ attn_bwd_long_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       tiles0 += nqt;
     }
   } else {
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(BL_REGS_OTHER));
-  if (warp == 13) {
-    if (elect_one()) {
-      // ------------------------------------------------------------------------------------ TMA producer
-      int rc = 0;  // ring position (blocks loaded so far)
-      for (int it = 0; it < num_its; ++it) {
-        const int kt = it % nkt, bh = static_cast<int>(blockIdx.x) + (it / nkt) * static_cast<int>(gridDim.x);
-        const int h = bh % H, b = bh / H;
-        const int kvb = it & 1;
-        uint8_t* kv = sKV + kvb * BL_KV_BYTES;
-        mbar_wait(&kv_empty[kvb], ((it >> 1) & 1) ^ 1);
-        mbar_arrive_expect_tx(&k_full[kvb], BL_TILE_BYTES);
-        tma_load_3d(kv, &tm_k, &k_full[kvb], h * BL_HD, kt * 128, b);
-        mbar_arrive_expect_tx(&v_full[kvb], BL_TILE_BYTES);
-        tma_load_3d(kv + BL_TILE_BYTES, &tm_v, &v_full[kvb], h * BL_HD, kt * 128, b);
-        for (int j = 0; j < J; ++j, ++rc) {
-          const int slot = rc % BL_RING_STAGES;
-          mbar_wait(&ring_empty[slot], ((rc / BL_RING_STAGES) & 1) ^ 1);
-          uint8_t* st = sRing + slot * BL_RING_BYTES;
-          mbar_arrive_expect_tx(&ring_full[slot], BL_RING_BYTES);
-          tma_load_3d(st, &tm_q, &ring_full[slot], h * BL_HD, j * 64, b);
-          tma_load_3d(st + BL_BLOCK_BYTES, &tm_do, &ring_full[slot], h * BL_HD, j * 64, b);
-        }
-      }
-    }
-    __syncwarp();
-  } else if (warp >= 14) {
-    // -------------------------------------------------------------------------------------- statistics loaders
-    // Per head, one head ahead of the compute warps: logsumexp (log2 domain) from global memory and
-    // delta[q] = sum_d dO[q, d] * O[q, d], computed here from the head's rows of O and dO (eight lanes per 128-byte row,
-    // four rows in flight per lane group) -- no separate delta kernel, no delta round trip through HBM.
-    const int t = threadIdx.x - 14 * 32;  // 0..63
-    const int grp = t >> 3, sub = t & 7;  // 8 row groups x 8 lanes
-    const int num_hd = num_its / nkt;
-    for (int hd = 0; hd < num_hd; ++hd) {
-      const int bh = static_cast<int>(blockIdx.x) + hd * static_cast<int>(gridDim.x);
-      const int h = bh % H, b = bh / H;
-      const int sb = hd & 1;
-      mbar_wait(&ld_empty[sb], ((hd >> 1) & 1) ^ 1);
-      const float* lrow = lse + static_cast<long long>(bh) * Nq;
-      for (int qi = t; qi < J * 64; qi += 64)
-        sL[sb * BL_NQ_MAX + qi] = qi < Nq ? __ldg(lrow + qi) * BL_LOG2E : INFINITY;  // exp2(-inf) = 0 for padded queries
-      const __nv_bfloat16* obase = o_rows + static_cast<long long>(b) * N * ldo + h * BL_HD + sub * 8;
-      const __nv_bfloat16* gbase = do_rows + static_cast<long long>(b) * N * lddo + h * BL_HD + sub * 8;
-      for (int base = 0; base < J * 64; base += 32) {
-        uint4 ov[4], gv[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int row = base + 8 * u + grp;
-          ov[u] = gv[u] = make_uint4(0u, 0u, 0u, 0u);
-          if (row < Nq) {
-            ov[u] = __ldg(reinterpret_cast<const uint4*>(obase + static_cast<long long>(row) * ldo));
-            gv[u] = __ldg(reinterpret_cast<const uint4*>(gbase + static_cast<long long>(row) * lddo));
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(BL_REGS_OTHER));
+    if (warp == 13) {
+      if (elect_one()) {
+        // ------------------------------------------------------------------------------------ TMA producer
+        int rc = 0;  // ring position (blocks loaded so far)
+        for (int it = 0; it < num_its; ++it) {
+          const int kt = it % nkt, bh = static_cast<int>(blockIdx.x) + (it / nkt) * static_cast<int>(gridDim.x);
+          const int h = bh % H, b = bh / H;
+          const int kvb = it & 1;
+          uint8_t* kv = sKV + kvb * BL_KV_BYTES;
+          mbar_wait(&kv_empty[kvb], ((it >> 1) & 1) ^ 1);
+          mbar_arrive_expect_tx(&k_full[kvb], BL_TILE_BYTES);
+          tma_load_3d(kv, &tm_k, &k_full[kvb], h * BL_HD, kt * 128, b);
+          mbar_arrive_expect_tx(&v_full[kvb], BL_TILE_BYTES);
+          tma_load_3d(kv + BL_TILE_BYTES, &tm_v, &v_full[kvb], h * BL_HD, kt * 128, b);
+          for (int j = 0; j < J; ++j, ++rc) {
+            const int slot = rc % BL_RING_STAGES;
+            mbar_wait(&ring_empty[slot], ((rc / BL_RING_STAGES) & 1) ^ 1);
+            uint8_t* st = sRing + slot * BL_RING_BYTES;
+            mbar_arrive_expect_tx(&ring_full[slot], BL_RING_BYTES);
+            tma_load_3d(st, &tm_q, &ring_full[slot], h * BL_HD, j * 64, b);
+            tma_load_3d(st + BL_BLOCK_BYTES, &tm_do, &ring_full[slot], h * BL_HD, j * 64, b);
           }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          float d0 = bf16_lo(ov[u].x) * bf16_lo(gv[u].x), d1 = bf16_hi(ov[u].x) * bf16_hi(gv[u].x);
-          d0 = fmaf(bf16_lo(ov[u].y), bf16_lo(gv[u].y), d0); d1 = fmaf(bf16_hi(ov[u].y), bf16_hi(gv[u].y), d1);
-          d0 = fmaf(bf16_lo(ov[u].z), bf16_lo(gv[u].z), d0); d1 = fmaf(bf16_hi(ov[u].z), bf16_hi(gv[u].z), d1);
-          d0 = fmaf(bf16_lo(ov[u].w), bf16_lo(gv[u].w), d0); d1 = fmaf(bf16_hi(ov[u].w), bf16_hi(gv[u].w), d1);
-          float d = d0 + d1;
-          d += __shfl_xor_sync(0xffffffffu, d, 1);
-          d += __shfl_xor_sync(0xffffffffu, d, 2);
-          d += __shfl_xor_sync(0xffffffffu, d, 4);
-          if (sub == 0) sD[sb * BL_NQ_MAX + base + 8 * u + grp] = d;   // rows past Nq: exact zeros
         }
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&ld_full[sb]);  // release semantics order the warp's stores before the arrival
-    }
-  } else if (warp == 8) {
-    if (elect_one()) {  // one issuing thread on the uniform datapath
-      // ------------------------------------------------------------------------------------ MMA issue loop
-      constexpr uint32_t idesc_ts = make_idesc_bf16(128, BL_HD, false, true);
-      constexpr uint32_t idesc_dq = make_idesc_bf16(128, BL_HD, true, true);
-      const uint32_t aRing = smem_u32(sRing), aS = smem_u32(sStage);
-      uint32_t ph_p = 0;  // bit b = parity of the next completion of bar_p[b]
-      int rc0 = 0;        // ring position of the item's first block
-      int g0 = 0;         // blocks processed before this item (score buffer = (g0 + j) & 1)
-      int tiles = 0;      // dQ products issued so far (dQ buffer / staging tile = tiles & 1)
-      for (int it = 0; it < num_its; ++it) {
-        const int kt = it % nkt;
-        const int kvb = it & 1;
-        const uint32_t aK = smem_u32(sKV + kvb * BL_KV_BYTES), aV = aK + BL_TILE_BYTES;
-        const uint64_t dK_ = make_smem_desc_sw128(aK, 0, 1024), dV_ = make_smem_desc_sw128(aV, 0, 1024);
-        const uint64_t dK_mn = make_smem_desc_sw128(aK, 8192, 1024);
-        auto issue_scores = [&](int j) {
-          const int buf = (g0 + j) & 1, r = rc0 + j, slot = r % BL_RING_STAGES;
-          const int w = j == J - 1 ? w_last : 64;
-          const uint32_t idesc = make_idesc_bf16(128, w, false, false);
-          const uint32_t aQ = aRing + slot * BL_RING_BYTES, aDO = aQ + BL_BLOCK_BYTES;
-          const uint64_t dQ_ = make_smem_desc_sw128(aQ, 0, 1024), dO_ = make_smem_desc_sw128(aDO, 0, 1024);
-          mbar_wait(&ring_full[slot], (r / BL_RING_STAGES) & 1);
-          if (j == 0) mbar_wait(&k_full[kvb], (it >> 1) & 1);
-          tc_fence_after();
+    } else if (warp >= 14) {
+      // -------------------------------------------------------------------------------------- statistics loaders
+      // Per head, one head ahead of the compute warps: logsumexp (log2 domain) from global memory and
+      // delta[q] = sum_d dO[q, d] * O[q, d], computed here from the head's rows of O and dO (eight lanes per 128-byte row,
+      // four rows in flight per lane group) -- no separate delta kernel, no delta round trip through HBM.
+      const int t = threadIdx.x - 14 * 32;  // 0..63
+      const int grp = t >> 3, sub = t & 7;  // 8 row groups x 8 lanes
+      const int num_hd = num_its / nkt;
+      for (int hd = 0; hd < num_hd; ++hd) {
+        const int bh = static_cast<int>(blockIdx.x) + hd * static_cast<int>(gridDim.x);
+        const int h = bh % H, b = bh / H;
+        const int sb = hd & 1;
+        mbar_wait(&ld_empty[sb], ((hd >> 1) & 1) ^ 1);
+        const float* lrow = lse + static_cast<long long>(bh) * Nq;
+        for (int qi = t; qi < J * 64; qi += 64)
+          sL[sb * BL_NQ_MAX + qi] = qi < Nq ? __ldg(lrow + qi) * BL_LOG2E : INFINITY;  // exp2(-inf) = 0 for padded queries
+        const __nv_bfloat16* obase = o_rows + static_cast<long long>(b) * N * ldo + h * BL_HD + sub * 8;
+        const __nv_bfloat16* gbase = do_rows + static_cast<long long>(b) * N * lddo + h * BL_HD + sub * 8;
+        for (int base = 0; base < J * 64; base += 32) {
+          uint4 ov[4], gv[4];
 #pragma unroll
-          for (int k = 0; k < BL_HD / 16; ++k) umma_bf16_ss(tmem_base + buf * 64, dK_ + 2 * k, dQ_ + 2 * k, idesc, k > 0 ? 1u : 0u);
-          if (j == 0) { mbar_wait(&v_full[kvb], (it >> 1) & 1); tc_fence_after(); }
+          for (int u = 0; u < 4; ++u) {
+            const int row = base + 8 * u + grp;
+            ov[u] = gv[u] = make_uint4(0u, 0u, 0u, 0u);
+            if (row < Nq) {
+              ov[u] = __ldg(reinterpret_cast<const uint4*>(obase + static_cast<long long>(row) * ldo));
+              gv[u] = __ldg(reinterpret_cast<const uint4*>(gbase + static_cast<long long>(row) * lddo));
+            }
+          }
 #pragma unroll
-          for (int k = 0; k < BL_HD / 16; ++k)
-            umma_bf16_ss(tmem_base + BL_COL_DP + buf * 64, dV_ + 2 * k, dO_ + 2 * k, idesc, k > 0 ? 1u : 0u);
-          umma_commit(&bar_s[buf]);
-        };
-        issue_scores(0);
-        if (J > 1) issue_scores(1);
-        for (int j = 0; j < J; ++j) {
-          const int buf = (g0 + j) & 1, r = rc0 + j, slot = r % BL_RING_STAGES;
-          BL_STAMP(64 + 4 * j);
-          mbar_wait(&bar_p[buf], (ph_p >> buf) & 1);
-          BL_STAMP(65 + 4 * j);
-          ph_p ^= 1u << buf;
-          tc_fence_after();
-          if (j == 0 && it > 0) {  // the previous item's dV / dK have left TMEM
-            mbar_wait(bar_free_vk, (it - 1) & 1);
+          for (int u = 0; u < 4; ++u) {
+            float d0 = bf16_lo(ov[u].x) * bf16_lo(gv[u].x), d1 = bf16_hi(ov[u].x) * bf16_hi(gv[u].x);
+            d0 = fmaf(bf16_lo(ov[u].y), bf16_lo(gv[u].y), d0); d1 = fmaf(bf16_hi(ov[u].y), bf16_hi(gv[u].y), d1);
+            d0 = fmaf(bf16_lo(ov[u].z), bf16_lo(gv[u].z), d0); d1 = fmaf(bf16_hi(ov[u].z), bf16_hi(gv[u].z), d1);
+            d0 = fmaf(bf16_lo(ov[u].w), bf16_lo(gv[u].w), d0); d1 = fmaf(bf16_hi(ov[u].w), bf16_hi(gv[u].w), d1);
+            float d = d0 + d1;
+            d += __shfl_xor_sync(0xffffffffu, d, 1);
+            d += __shfl_xor_sync(0xffffffffu, d, 2);
+            d += __shfl_xor_sync(0xffffffffu, d, 4);
+            if (sub == 0) sD[sb * BL_NQ_MAX + base + 8 * u + grp] = d;   // rows past Nq: exact zeros
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ld_full[sb]);  // release semantics order the warp's stores before the arrival
+      }
+    } else if (warp == 8) {
+      if (elect_one()) {  // one issuing thread on the uniform datapath
+        // ------------------------------------------------------------------------------------ MMA issue loop
+        constexpr uint32_t idesc_ts = make_idesc_bf16(128, BL_HD, false, true);
+        constexpr uint32_t idesc_dq = make_idesc_bf16(128, BL_HD, true, true);
+        const uint32_t aRing = smem_u32(sRing), aS = smem_u32(sStage);
+        uint32_t ph_p = 0;  // bit b = parity of the next completion of bar_p[b]
+        int rc0 = 0;        // ring position of the item's first block
+        int g0 = 0;         // blocks processed before this item (score buffer = (g0 + j) & 1)
+        int tiles = 0;      // dQ products issued so far (dQ buffer / staging tile = tiles & 1)
+        for (int it = 0; it < num_its; ++it) {
+          const int kt = it % nkt;
+          const int kvb = it & 1;
+          const uint32_t aK = smem_u32(sKV + kvb * BL_KV_BYTES), aV = aK + BL_TILE_BYTES;
+          const uint64_t dK_ = make_smem_desc_sw128(aK, 0, 1024), dV_ = make_smem_desc_sw128(aV, 0, 1024);
+          const uint64_t dK_mn = make_smem_desc_sw128(aK, 8192, 1024);
+          auto issue_scores = [&](int j) {
+            const int buf = (g0 + j) & 1, r = rc0 + j, slot = r % BL_RING_STAGES;
+            const int w = j == J - 1 ? w_last : 64;
+            const uint32_t idesc = make_idesc_bf16(128, w, false, false);
+            const uint32_t aQ = aRing + slot * BL_RING_BYTES, aDO = aQ + BL_BLOCK_BYTES;
+            const uint64_t dQ_ = make_smem_desc_sw128(aQ, 0, 1024), dO_ = make_smem_desc_sw128(aDO, 0, 1024);
+            mbar_wait(&ring_full[slot], (r / BL_RING_STAGES) & 1);
+            if (j == 0) mbar_wait(&k_full[kvb], (it >> 1) & 1);
             tc_fence_after();
-          }
-          const int ksteps = (j == J - 1 ? w_last : 64) >> 4;
-          const uint32_t aQ = aRing + slot * BL_RING_BYTES, aDO = aQ + BL_BLOCK_BYTES;
-          const uint64_t dO_mn = make_smem_desc_sw128(aDO, 8192, 1024);
-          const uint64_t dQ_mn = make_smem_desc_sw128(aQ, 8192, 1024);
-          for (int k = 0; k < ksteps; ++k) {  // dV += P^T dO
-            const uint32_t a = tmem_base + buf * 64 + (k >> 1) * 32 + (k & 1) * 8;
-            umma_bf16_ts(tmem_base + BL_COL_DV, a, dO_mn + 128 * k, idesc_ts, (j > 0 || k > 0) ? 1u : 0u);
-          }
-          for (int k = 0; k < ksteps; ++k) {  // dK += dS^T Q
-            const uint32_t a = tmem_base + BL_COL_DP + buf * 64 + (k >> 1) * 32 + (k & 1) * 8;
-            umma_bf16_ts(tmem_base + BL_COL_DK, a, dQ_mn + 128 * k, idesc_ts, (j > 0 || k > 0) ? 1u : 0u);
-          }
-          umma_commit(&ring_empty[slot]);  // this block of Q / dO has been consumed once these complete
-          // the P^T / dS^T columns of this buffer have been consumed (in issue order): refill it with the scores of
-          // block j+2 before the dQ product, which the compute warps do not wait for
-          BL_STAMP(66 + 4 * j);
-          if (j + 2 < J) issue_scores(j + 2);
-          BL_STAMP(67 + 4 * j);
-          if ((j & 1) || j == J - 1) {  // dQ partial of this query tile: dS K over this item's key tile
-            const int dqb = tiles & 1;
-            if (tiles >= 2) {  // the drain warps have read the product issued two tiles ago out of this buffer
-              mbar_wait(&bar_free_q[dqb], ((tiles >> 1) - 1) & 1);
+#pragma unroll
+            for (int k = 0; k < BL_HD / 16; ++k) umma_bf16_ss(tmem_base + buf * 64, dK_ + 2 * k, dQ_ + 2 * k, idesc, k > 0 ? 1u : 0u);
+            if (j == 0) { mbar_wait(&v_full[kvb], (it >> 1) & 1); tc_fence_after(); }
+#pragma unroll
+            for (int k = 0; k < BL_HD / 16; ++k)
+              umma_bf16_ss(tmem_base + BL_COL_DP + buf * 64, dV_ + 2 * k, dO_ + 2 * k, idesc, k > 0 ? 1u : 0u);
+            umma_commit(&bar_s[buf]);
+          };
+          issue_scores(0);
+          if (J > 1) issue_scores(1);
+          for (int j = 0; j < J; ++j) {
+            const int buf = (g0 + j) & 1, r = rc0 + j, slot = r % BL_RING_STAGES;
+            BL_STAMP(64 + 4 * j);
+            mbar_wait(&bar_p[buf], (ph_p >> buf) & 1);
+            BL_STAMP(65 + 4 * j);
+            ph_p ^= 1u << buf;
+            tc_fence_after();
+            if (j == 0 && it > 0) {  // the previous item's dV / dK have left TMEM
+              mbar_wait(bar_free_vk, (it - 1) & 1);
               tc_fence_after();
             }
-            const int kvalid = min(128, N - kt * 128);
-            const int ks = (kvalid + 15) >> 4;
-            const uint64_t dS_mn = make_smem_desc_sw128(aS + dqb * BL_STAGE_BYTES, 16384, 1024);
-            for (int k = 0; k < ks; ++k)
-              umma_bf16_ss(tmem_base + BL_COL_DQ + dqb * 64, dS_mn + 128 * k, dK_mn + 128 * k, idesc_dq, k > 0 ? 1u : 0u);
-            umma_commit(&bar_dq[dqb]);
-            ++tiles;
+            const int ksteps = (j == J - 1 ? w_last : 64) >> 4;
+            const uint32_t aQ = aRing + slot * BL_RING_BYTES, aDO = aQ + BL_BLOCK_BYTES;
+            const uint64_t dO_mn = make_smem_desc_sw128(aDO, 8192, 1024);
+            const uint64_t dQ_mn = make_smem_desc_sw128(aQ, 8192, 1024);
+            for (int k = 0; k < ksteps; ++k) {  // dV += P^T dO
+              const uint32_t a = tmem_base + buf * 64 + (k >> 1) * 32 + (k & 1) * 8;
+              umma_bf16_ts(tmem_base + BL_COL_DV, a, dO_mn + 128 * k, idesc_ts, (j > 0 || k > 0) ? 1u : 0u);
+            }
+            for (int k = 0; k < ksteps; ++k) {  // dK += dS^T Q
+              const uint32_t a = tmem_base + BL_COL_DP + buf * 64 + (k >> 1) * 32 + (k & 1) * 8;
+              umma_bf16_ts(tmem_base + BL_COL_DK, a, dQ_mn + 128 * k, idesc_ts, (j > 0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit(&ring_empty[slot]);  // this block of Q / dO has been consumed once these complete
+            // the P^T / dS^T columns of this buffer have been consumed (in issue order): refill it with the scores of
+            // block j+2 before the dQ product, which the compute warps do not wait for
+            BL_STAMP(66 + 4 * j);
+            if (j + 2 < J) issue_scores(j + 2);
+            BL_STAMP(67 + 4 * j);
+            if ((j & 1) || j == J - 1) {  // dQ partial of this query tile: dS K over this item's key tile
+              const int dqb = tiles & 1;
+              if (tiles >= 2) {  // the drain warps have read the product issued two tiles ago out of this buffer
+                mbar_wait(&bar_free_q[dqb], ((tiles >> 1) - 1) & 1);
+                tc_fence_after();
+              }
+              const int kvalid = min(128, N - kt * 128);
+              const int ks = (kvalid + 15) >> 4;
+              const uint64_t dS_mn = make_smem_desc_sw128(aS + dqb * BL_STAGE_BYTES, 16384, 1024);
+              for (int k = 0; k < ks; ++k)
+                umma_bf16_ss(tmem_base + BL_COL_DQ + dqb * 64, dS_mn + 128 * k, dK_mn + 128 * k, idesc_dq, k > 0 ? 1u : 0u);
+              umma_commit(&bar_dq[dqb]);
+              ++tiles;
+            }
+            if (j == J - 1) {
+              umma_commit(bar_acc);           // dV / dK of this key tile are complete
+              umma_commit(&kv_empty[kvb]);    // and nothing reads this K / V buffer any more
+            }
           }
-          if (j == J - 1) {
-            umma_commit(bar_acc);           // dV / dK of this key tile are complete
-            umma_commit(&kv_empty[kvb]);    // and nothing reads this K / V buffer any more
-          }
+          rc0 += J;
+          g0 += J;
         }
-        rc0 += J;
-        g0 += J;
       }
-    }
-    __syncwarp();
-  } else if (warp < 13) {
-    // -------------------------------------------------------------------------------------- drain warps
-    const int quad = warp & 3;  // warps 9, 10, 11, 12 -> TMEM lane quadrants 1, 2, 3, 0
-    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
-    const uint32_t stage = smem_u32(sOut) + (warp - 9) * 4096;  // two 2 KB tiles: [32 rows][64 B], 64-byte swizzle
-    const int r = quad * 32 + lane;
-    // this CTA's private fp32 dQ slab: [query tile][quadrant][half][8 column groups][32 lanes][4 floats] -- every warp
-    // access is 512 contiguous bytes, and an element is only ever touched by the thread that owns its (row, columns)
-    float* slab = dq_scratch + static_cast<long long>(blockIdx.x) * (BL_NQ_MAX * BL_HD);
-    int tiles = 0;
-    for (int it = 0; it < num_its; ++it) {
-      const int kt = it % nkt, bh = static_cast<int>(blockIdx.x) + (it / nkt) * static_cast<int>(gridDim.x);
-      const int h = bh % H, b = bh / H;
-      // 32 rows x 32 packed bf16 columns -> staging slot (64-byte swizzle); optional column sums into a bias gradient
-      auto stage_packed = [&](int slot, const uint32_t (&pk)[16], bool valid, float* bias_dst, int half) {
-        const uint32_t base = stage + slot * 2048 + lane * 64;
-        const int x = (lane >> 1) & 3;
+      __syncwarp();
+    } else if (warp < 13) {
+      // -------------------------------------------------------------------------------------- drain warps
+      const int quad = warp & 3;  // warps 9, 10, 11, 12 -> TMEM lane quadrants 1, 2, 3, 0
+      const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+      const uint32_t stage = smem_u32(sOut) + (warp - 9) * 4096;  // two 2 KB tiles: [32 rows][64 B], 64-byte swizzle
+      const int r = quad * 32 + lane;
+      // this CTA's private fp32 dQ slab: [query tile][quadrant][half][8 column groups][32 lanes][4 floats] -- every warp
+      // access is 512 contiguous bytes, and an element is only ever touched by the thread that owns its (row, columns)
+      float* slab = dq_scratch + static_cast<long long>(blockIdx.x) * (BL_NQ_MAX * BL_HD);
+      int tiles = 0;
+      for (int it = 0; it < num_its; ++it) {
+        const int kt = it % nkt, bh = static_cast<int>(blockIdx.x) + (it / nkt) * static_cast<int>(gridDim.x);
+        const int h = bh % H, b = bh / H;
+        // 32 rows x 32 packed bf16 columns -> staging slot (64-byte swizzle); optional column sums into a bias gradient
+        auto stage_packed = [&](int slot, const uint32_t (&pk)[16], bool valid, float* bias_dst, int half) {
+          const uint32_t base = stage + slot * 2048 + lane * 64;
+          const int x = (lane >> 1) & 3;
 #pragma unroll
-        for (int pc = 0; pc < 4; ++pc)
-          bl_st_shared_v4(base + ((pc ^ x) << 4), pk[4 * pc], pk[4 * pc + 1], pk[4 * pc + 2], pk[4 * pc + 3]);
-        if (bias_dst != nullptr) {
-          float v[32];
+          for (int pc = 0; pc < 4; ++pc)
+            bl_st_shared_v4(base + ((pc ^ x) << 4), pk[4 * pc], pk[4 * pc + 1], pk[4 * pc + 2], pk[4 * pc + 3]);
+          if (bias_dst != nullptr) {
+            float v[32];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            v[2 * i] = valid ? bf16_lo(pk[i]) : 0.f;
-            v[2 * i + 1] = valid ? bf16_hi(pk[i]) : 0.f;
+            for (int i = 0; i < 16; ++i) {
+              v[2 * i] = valid ? bf16_lo(pk[i]) : 0.f;
+              v[2 * i + 1] = valid ? bf16_hi(pk[i]) : 0.f;
+            }
+            const float cs = bl_warp_colsum32(v, lane);
+            atomicAdd(bias_dst + h * BL_HD + half * 32 + lane, cs);
           }
-          const float cs = bl_warp_colsum32(v, lane);
-          atomicAdd(bias_dst + h * BL_HD + half * 32 + lane, cs);
-        }
-      };
-      // One half tile (32 rows x 32 fp32 accumulator columns of this warp's lane quadrant): TMEM -> scaled, packed bf16
-      auto stage_half = [&](int slot, uint32_t col, float f, bool valid, float* bias_dst, int half) {
-        uint32_t rr[32];
-        tmem_ld_32x32b_x32(lane_addr + col, rr);
-        tmem_ld_wait();
-        uint32_t pk[16];
+        };
+        // One half tile (32 rows x 32 fp32 accumulator columns of this warp's lane quadrant): TMEM -> scaled, packed bf16
+        auto stage_half = [&](int slot, uint32_t col, float f, bool valid, float* bias_dst, int half) {
+          uint32_t rr[32];
+          tmem_ld_32x32b_x32(lane_addr + col, rr);
+          tmem_ld_wait();
+          uint32_t pk[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(__uint_as_float(rr[2 * i]) * f, __uint_as_float(rr[2 * i + 1]) * f);
-        stage_packed(slot, pk, valid, bias_dst, half);
-      };
-      const bool first_kt = kt == 0, last_kt = kt == nkt - 1;
-      for (int qt = 0; qt < nqt; ++qt, ++tiles) {  // dQ contribution of each query tile as its product completes
-        const int dqb = tiles & 1;
-        const bool active = qt * 128 + quad * 32 < Nq;
-        float4 acc_next[4];
-        if (active && !first_kt) {  // this thread's slab values of the tile's first quarter: in flight under the wait
-          const float4* sp0 = reinterpret_cast<const float4*>(slab + ((qt * 4 + quad) * 4) * 512) + lane;
+          for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(__uint_as_float(rr[2 * i]) * f, __uint_as_float(rr[2 * i + 1]) * f);
+          stage_packed(slot, pk, valid, bias_dst, half);
+        };
+        const bool first_kt = kt == 0, last_kt = kt == nkt - 1;
+        for (int qt = 0; qt < nqt; ++qt, ++tiles) {  // dQ contribution of each query tile as its product completes
+          const int dqb = tiles & 1;
+          const bool active = qt * 128 + quad * 32 < Nq;
+          float4 acc_next[4];
+          if (active && !first_kt) {  // this thread's slab values of the tile's first quarter: in flight under the wait
+            const float4* sp0 = reinterpret_cast<const float4*>(slab + ((qt * 4 + quad) * 4) * 512) + lane;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) acc_next[i] = __ldcg(sp0 + i * 32);
-        }
-        if (warp == 12 && lane == 0) BL_STAMP(112 + 2 * qt);
-        mbar_wait(&bar_dq[dqb], (tiles >> 1) & 1);
-        if (warp == 12 && lane == 0) BL_STAMP(113 + 2 * qt);
-        tc_fence_after();
-        if (last_kt) {
-          if (lane == 0) tma_store_wait_read<0>();  // this warp's staging slots are free again
-          __syncwarp();
-        }
-        if (active) {
-          float* qdst = (last_kt && (bias_mask & 1)) ? bias_grad : nullptr;
-          const bool row_ok = qt * 128 + r < Nq;
-          // 16 accumulator columns at a time (the drain warps live within 88 registers); the slab loads of a quarter are
-          // issued one quarter ahead (the first before the product is even complete), so their L2 latency is hidden
+            for (int i = 0; i < 4; ++i) acc_next[i] = __ldcg(sp0 + i * 32);
+          }
+          if (warp == 12 && lane == 0) BL_STAMP(112 + 2 * qt);
+          mbar_wait(&bar_dq[dqb], (tiles >> 1) & 1);
+          if (warp == 12 && lane == 0) BL_STAMP(113 + 2 * qt);
+          tc_fence_after();
+          if (last_kt) {
+            if (lane == 0) tma_store_wait_read<0>();  // this warp's staging slots are free again
+            __syncwarp();
+          }
+          if (active) {
+            float* qdst = (last_kt && (bias_mask & 1)) ? bias_grad : nullptr;
+            const bool row_ok = qt * 128 + r < Nq;
+            // 16 accumulator columns at a time (the drain warps live within 88 registers); the slab loads of a quarter are
+            // issued one quarter ahead (the first before the product is even complete), so their L2 latency is hidden
 #pragma unroll 1
-          for (int qr = 0; qr < 4; ++qr) {
-            float4* sp = reinterpret_cast<float4*>(slab + ((qt * 4 + quad) * 4 + qr) * 512) + lane;
-            float4 acc[4];
+            for (int qr = 0; qr < 4; ++qr) {
+              float4* sp = reinterpret_cast<float4*>(slab + ((qt * 4 + quad) * 4 + qr) * 512) + lane;
+              float4 acc[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) acc[i] = acc_next[i];
-            if (!first_kt && qr < 3) {
+              for (int i = 0; i < 4; ++i) acc[i] = acc_next[i];
+              if (!first_kt && qr < 3) {
 #pragma unroll
-              for (int i = 0; i < 4; ++i) acc_next[i] = __ldcg(sp + 128 + i * 32);
-            }
-            uint32_t rr[16];
-            tmem_ld_32x32b_x16(lane_addr + BL_COL_DQ + dqb * 64 + qr * 16, rr);
-            tmem_ld_wait();
-            if (!first_kt) {
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                rr[4 * i + 0] = __float_as_uint(__uint_as_float(rr[4 * i + 0]) + acc[i].x);
-                rr[4 * i + 1] = __float_as_uint(__uint_as_float(rr[4 * i + 1]) + acc[i].y);
-                rr[4 * i + 2] = __float_as_uint(__uint_as_float(rr[4 * i + 2]) + acc[i].z);
-                rr[4 * i + 3] = __float_as_uint(__uint_as_float(rr[4 * i + 3]) + acc[i].w);
+                for (int i = 0; i < 4; ++i) acc_next[i] = __ldcg(sp + 128 + i * 32);
               }
-            }
-            if (!last_kt) {
+              uint32_t rr[16];
+              tmem_ld_32x32b_x16(lane_addr + BL_COL_DQ + dqb * 64 + qr * 16, rr);
+              tmem_ld_wait();
+              if (!first_kt) {
 #pragma unroll
-              for (int i = 0; i < 4; ++i)
-                __stcg(sp + i * 32, make_float4(__uint_as_float(rr[4 * i]), __uint_as_float(rr[4 * i + 1]),
-                                                __uint_as_float(rr[4 * i + 2]), __uint_as_float(rr[4 * i + 3])));
-            } else {
-              // scale, round to bf16, stage: quarter qr = 16-byte chunks (qr & 1) * 2 + {0, 1} of slot qr >> 1
-              const uint32_t p0 = pack_bf16x2(__uint_as_float(rr[0]) * scale, __uint_as_float(rr[1]) * scale);
-              const uint32_t p1 = pack_bf16x2(__uint_as_float(rr[2]) * scale, __uint_as_float(rr[3]) * scale);
-              const uint32_t p2 = pack_bf16x2(__uint_as_float(rr[4]) * scale, __uint_as_float(rr[5]) * scale);
-              const uint32_t p3 = pack_bf16x2(__uint_as_float(rr[6]) * scale, __uint_as_float(rr[7]) * scale);
-              const uint32_t p4 = pack_bf16x2(__uint_as_float(rr[8]) * scale, __uint_as_float(rr[9]) * scale);
-              const uint32_t p5 = pack_bf16x2(__uint_as_float(rr[10]) * scale, __uint_as_float(rr[11]) * scale);
-              const uint32_t p6 = pack_bf16x2(__uint_as_float(rr[12]) * scale, __uint_as_float(rr[13]) * scale);
-              const uint32_t p7 = pack_bf16x2(__uint_as_float(rr[14]) * scale, __uint_as_float(rr[15]) * scale);
-              const uint32_t base = stage + (qr >> 1) * 2048 + lane * 64;
-              const int x = (lane >> 1) & 3, pc = (qr & 1) * 2;
-              bl_st_shared_v4(base + ((pc ^ x) << 4), p0, p1, p2, p3);
-              bl_st_shared_v4(base + (((pc + 1) ^ x) << 4), p4, p5, p6, p7);
-              if (qdst != nullptr) {
-                float v[16];
-                const uint32_t pk[8] = {p0, p1, p2, p3, p4, p5, p6, p7};
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  v[2 * i] = row_ok ? bf16_lo(pk[i]) : 0.f;
-                  v[2 * i + 1] = row_ok ? bf16_hi(pk[i]) : 0.f;
+                for (int i = 0; i < 4; ++i) {
+                  rr[4 * i + 0] = __float_as_uint(__uint_as_float(rr[4 * i + 0]) + acc[i].x);
+                  rr[4 * i + 1] = __float_as_uint(__uint_as_float(rr[4 * i + 1]) + acc[i].y);
+                  rr[4 * i + 2] = __float_as_uint(__uint_as_float(rr[4 * i + 2]) + acc[i].z);
+                  rr[4 * i + 3] = __float_as_uint(__uint_as_float(rr[4 * i + 3]) + acc[i].w);
                 }
-                // recursive halving over 16 columns, then the two half-warps are added: lane i < 16 holds column i
+              }
+              if (!last_kt) {
 #pragma unroll
-                for (int sft = 8; sft >= 1; sft >>= 1) {
-                  const bool upper = (lane & sft) != 0;
+                for (int i = 0; i < 4; ++i)
+                  __stcg(sp + i * 32, make_float4(__uint_as_float(rr[4 * i]), __uint_as_float(rr[4 * i + 1]),
+                                                  __uint_as_float(rr[4 * i + 2]), __uint_as_float(rr[4 * i + 3])));
+              } else {
+                // scale, round to bf16, stage: quarter qr = 16-byte chunks (qr & 1) * 2 + {0, 1} of slot qr >> 1
+                const uint32_t p0 = pack_bf16x2(__uint_as_float(rr[0]) * scale, __uint_as_float(rr[1]) * scale);
+                const uint32_t p1 = pack_bf16x2(__uint_as_float(rr[2]) * scale, __uint_as_float(rr[3]) * scale);
+                const uint32_t p2 = pack_bf16x2(__uint_as_float(rr[4]) * scale, __uint_as_float(rr[5]) * scale);
+                const uint32_t p3 = pack_bf16x2(__uint_as_float(rr[6]) * scale, __uint_as_float(rr[7]) * scale);
+                const uint32_t p4 = pack_bf16x2(__uint_as_float(rr[8]) * scale, __uint_as_float(rr[9]) * scale);
+                const uint32_t p5 = pack_bf16x2(__uint_as_float(rr[10]) * scale, __uint_as_float(rr[11]) * scale);
+                const uint32_t p6 = pack_bf16x2(__uint_as_float(rr[12]) * scale, __uint_as_float(rr[13]) * scale);
+                const uint32_t p7 = pack_bf16x2(__uint_as_float(rr[14]) * scale, __uint_as_float(rr[15]) * scale);
+                const uint32_t base = stage + (qr >> 1) * 2048 + lane * 64;
+                const int x = (lane >> 1) & 3, pc = (qr & 1) * 2;
+                bl_st_shared_v4(base + ((pc ^ x) << 4), p0, p1, p2, p3);
+                bl_st_shared_v4(base + (((pc + 1) ^ x) << 4), p4, p5, p6, p7);
+                if (qdst != nullptr) {
+                  float v[16];
+                  const uint32_t pk[8] = {p0, p1, p2, p3, p4, p5, p6, p7};
 #pragma unroll
-                  for (int i = 0; i < sft; ++i) {
-                    const float send = upper ? v[i] : v[i + sft];
-                    const float keep = upper ? v[i + sft] : v[i];
-                    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, sft);
+                  for (int i = 0; i < 8; ++i) {
+                    v[2 * i] = row_ok ? bf16_lo(pk[i]) : 0.f;
+                    v[2 * i + 1] = row_ok ? bf16_hi(pk[i]) : 0.f;
                   }
+                  // recursive halving over 16 columns, then the two half-warps are added: lane i < 16 holds column i
+#pragma unroll
+                  for (int sft = 8; sft >= 1; sft >>= 1) {
+                    const bool upper = (lane & sft) != 0;
+#pragma unroll
+                    for (int i = 0; i < sft; ++i) {
+                      const float send = upper ? v[i] : v[i + sft];
+                      const float keep = upper ? v[i + sft] : v[i];
+                      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, sft);
+                    }
+                  }
+                  const float cs = v[0] + __shfl_xor_sync(0xffffffffu, v[0], 16);
+                  if (lane < 16) atomicAdd(qdst + h * BL_HD + qr * 16 + lane, cs);
                 }
-                const float cs = v[0] + __shfl_xor_sync(0xffffffffu, v[0], 16);
-                if (lane < 16) atomicAdd(qdst + h * BL_HD + qr * 16 + lane, cs);
               }
             }
+            if (last_kt) fence_proxy_async();
           }
-          if (last_kt) fence_proxy_async();
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(&bar_free_q[dqb]);
-          if (active && last_kt) {
-            tma_store_3d_addr(&tm_dq, stage, h * BL_HD, qt * 128 + quad * 32, b);
-            tma_store_3d_addr(&tm_dq, stage + 2048, h * BL_HD + 32, qt * 128 + quad * 32, b);
-            tma_store_commit();
-          }
-        }
-      }
-      {  // dV, then dK of the item's key tile (two staging slots: one tensor at a time)
-        const bool quad_active = kt * 128 + quad * 32 < N;
-        const int row0 = kt * 128 + quad * 32;
-        const bool valid = kt * 128 + r < N;
-        float* vdst = (bias_mask & 4) ? bias_grad + 2 * H * BL_HD : nullptr;
-        float* kdst = (bias_mask & 2) ? bias_grad + H * BL_HD : nullptr;
-        mbar_wait(bar_acc, it & 1);
-        tc_fence_after();
-        if (lane == 0) tma_store_wait_read<0>();
-        __syncwarp();
-        if (quad_active) {
-          stage_half(0, BL_COL_DV, 1.0f, valid, vdst, 0);
-          stage_half(1, BL_COL_DV + 32, 1.0f, valid, vdst, 1);
-          fence_proxy_async();
+          tc_fence_before();
           __syncwarp();
           if (lane == 0) {
-            tma_store_3d_addr(&tm_dv, stage, h * BL_HD, row0, b);
-            tma_store_3d_addr(&tm_dv, stage + 2048, h * BL_HD + 32, row0, b);
-            tma_store_commit();
-            tma_store_wait_read<0>();
+            mbar_arrive(&bar_free_q[dqb]);
+            if (active && last_kt) {
+              tma_store_3d_addr(&tm_dq, stage, h * BL_HD, qt * 128 + quad * 32, b);
+              tma_store_3d_addr(&tm_dq, stage + 2048, h * BL_HD + 32, qt * 128 + quad * 32, b);
+              tma_store_commit();
+            }
           }
-          __syncwarp();
-          stage_half(0, BL_COL_DK, scale, valid, kdst, 0);
-          stage_half(1, BL_COL_DK + 32, scale, valid, kdst, 1);
-          fence_proxy_async();
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(bar_free_vk);  // the MMA thread may overwrite dV / dK
+        {  // dV, then dK of the item's key tile (two staging slots: one tensor at a time)
+          const bool quad_active = kt * 128 + quad * 32 < N;
+          const int row0 = kt * 128 + quad * 32;
+          const bool valid = kt * 128 + r < N;
+          float* vdst = (bias_mask & 4) ? bias_grad + 2 * H * BL_HD : nullptr;
+          float* kdst = (bias_mask & 2) ? bias_grad + H * BL_HD : nullptr;
+          mbar_wait(bar_acc, it & 1);
+          tc_fence_after();
+          if (lane == 0) tma_store_wait_read<0>();
+          __syncwarp();
           if (quad_active) {
-            tma_store_3d_addr(&tm_dk, stage, h * BL_HD, row0, b);
-            tma_store_3d_addr(&tm_dk, stage + 2048, h * BL_HD + 32, row0, b);
-            tma_store_commit();
+            stage_half(0, BL_COL_DV, 1.0f, valid, vdst, 0);
+            stage_half(1, BL_COL_DV + 32, 1.0f, valid, vdst, 1);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_3d_addr(&tm_dv, stage, h * BL_HD, row0, b);
+              tma_store_3d_addr(&tm_dv, stage + 2048, h * BL_HD + 32, row0, b);
+              tma_store_commit();
+              tma_store_wait_read<0>();
+            }
+            __syncwarp();
+            stage_half(0, BL_COL_DK, scale, valid, kdst, 0);
+            stage_half(1, BL_COL_DK + 32, scale, valid, kdst, 1);
+            fence_proxy_async();
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive(bar_free_vk);  // the MMA thread may overwrite dV / dK
+            if (quad_active) {
+              tma_store_3d_addr(&tm_dk, stage, h * BL_HD, row0, b);
+              tma_store_3d_addr(&tm_dk, stage + 2048, h * BL_HD + 32, row0, b);
+              tma_store_commit();
+            }
           }
         }
       }
+      if (lane == 0) tma_store_wait_read<0>();  // the staging tiles must outlive the last TMA stores
     }
-    if (lane == 0) tma_store_wait_read<0>();  // the staging tiles must outlive the last TMA stores
-  }
   }  // roles other than the compute warps
   tc_fence_before();
   __syncthreads();

@@ -233,130 +233,130 @@ attn_fwd_fused_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     if (warp < 4) engine(std::integral_constant<int, 0>{});
     else engine(std::integral_constant<int, 1>{});
   } else {
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(FF_REGS_OTHER));
-  if (warp == FF_ISSUE_WARP) {
-    if (elect_one()) {
-      // ------------------------------------------------------------------------------ TMA + MMA issue thread
-      const uint32_t idesc_s = make_idesc_bf16(128, nk, false, false);
-      constexpr uint32_t idesc_o = make_idesc_bf16(128, FF_HD, false, true);
-      auto issue_loads = [&](int item, int stage) {
-        const int h = item % H, b = item / H;
-        uint8_t* st = smem + stage * FF_STAGE_BYTES;
-        mbar_arrive_expect_tx(&bar_ld[stage], FF_STAGE_BYTES);
-        tma_load_3d(st + FF_Q_BYTES, &tm_k, &bar_ld[stage], h * FF_HD, 0, b);
-        tma_load_3d(st, &tm_q, &bar_ld[stage], h * FF_HD, 0, b);
-        tma_load_3d(st + FF_Q_BYTES + FF_KV_BYTES, &tm_v, &bar_ld[stage], h * FF_HD, 0, b);
-      };
-      // P V of unit u: P from the head of TMEM buffer u & 1, V from operand stage `stage`, O into the buffer's tail
-      auto issue_pv = [&](int u, int stage) {
-        const int b = u & 1;
-        mbar_wait(&bar_p[b], par(u));
-        tc_fence_after();
-        FF_STAMP(u, 1);
-        const uint64_t dv = make_smem_desc_sw128(smem_u32(smem + stage * FF_STAGE_BYTES) + FF_Q_BYTES + FF_KV_BYTES, 8192, 1024);
-        for (int k = 0; k < n16; ++k)
-          umma_bf16_ts(tmem_base + b * 256 + FF_O_COL, tmem_base + b * 256 + 8 * k, dv + 128 * k, idesc_o, k > 0 ? 1u : 0u);
-        umma_commit(&bar_o[b]);
-      };
-      issue_loads(blockIdx.x, 0);
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(FF_REGS_OTHER));
+    if (warp == FF_ISSUE_WARP) {
+      if (elect_one()) {
+        // ------------------------------------------------------------------------------ TMA + MMA issue thread
+        const uint32_t idesc_s = make_idesc_bf16(128, nk, false, false);
+        constexpr uint32_t idesc_o = make_idesc_bf16(128, FF_HD, false, true);
+        auto issue_loads = [&](int item, int stage) {
+          const int h = item % H, b = item / H;
+          uint8_t* st = smem + stage * FF_STAGE_BYTES;
+          mbar_arrive_expect_tx(&bar_ld[stage], FF_STAGE_BYTES);
+          tma_load_3d(st + FF_Q_BYTES, &tm_k, &bar_ld[stage], h * FF_HD, 0, b);
+          tma_load_3d(st, &tm_q, &bar_ld[stage], h * FF_HD, 0, b);
+          tma_load_3d(st + FF_Q_BYTES + FF_KV_BYTES, &tm_v, &bar_ld[stage], h * FF_HD, 0, b);
+        };
+        // P V of unit u: P from the head of TMEM buffer u & 1, V from operand stage `stage`, O into the buffer's tail
+        auto issue_pv = [&](int u, int stage) {
+          const int b = u & 1;
+          mbar_wait(&bar_p[b], par(u));
+          tc_fence_after();
+          FF_STAMP(u, 1);
+          const uint64_t dv = make_smem_desc_sw128(smem_u32(smem + stage * FF_STAGE_BYTES) + FF_Q_BYTES + FF_KV_BYTES, 8192, 1024);
+          for (int k = 0; k < n16; ++k)
+            umma_bf16_ts(tmem_base + b * 256 + FF_O_COL, tmem_base + b * 256 + 8 * k, dv + 128 * k, idesc_o, k > 0 ? 1u : 0u);
+          umma_commit(&bar_o[b]);
+        };
+        issue_loads(blockIdx.x, 0);
+        int u = 0;
+        int prev_stage = 0;
+        for (int it = 0, item = blockIdx.x; item < num_items; ++it, item += gridDim.x) {
+          const int stage = it & 1;
+          const uint32_t aQ = smem_u32(smem + stage * FF_STAGE_BYTES), aK = aQ + FF_Q_BYTES;
+          const uint64_t dk = make_smem_desc_sw128(aK, 0, 1024);
+          const bool has_next = item + static_cast<int>(gridDim.x) < num_items;
+          for (int t = 0; t < nqt; ++t, ++u) {
+            const int b = u & 1;
+            // buffer b is free for S(u) once O(u-2) has been drained out of its tail (P V(u-2) then has completed too)
+            if (u >= 2) mbar_wait(&bar_ofree[b], par(u - 2));
+            if (t == 0) mbar_wait(&bar_ld[stage], (it >> 1) & 1);
+            tc_fence_after();
+            const uint64_t dq = make_smem_desc_sw128(aQ + t * 16384, 0, 1024);
+#pragma unroll
+            for (int k = 0; k < FF_HD / 16; ++k) umma_bf16_ss(tmem_base + b * 256, dq + 2 * k, dk + 2 * k, idesc_s, k > 0 ? 1u : 0u);
+            umma_commit(&bar_s[b]);
+            FF_STAMP(u, 0);
+            // Prefetch the next item into the other operand stage once every MMA that read it has completed. Two tiles
+            // per item: those are units u-3 and u-2, and the drain of unit u-2 was awaited above. One tile per item: the
+            // reader is unit u-1, whose P V is only issued below -- prefetch after it has completed.
+            if (nqt == 2 && t == 1 && has_next) issue_loads(item + gridDim.x, stage ^ 1);
+            if (u >= 1) issue_pv(u - 1, t == 0 ? prev_stage : stage);
+            if (nqt == 1 && has_next) {
+              if (u >= 1) mbar_wait(&bar_o[b ^ 1], par(u - 1));
+              issue_loads(item + gridDim.x, stage ^ 1);
+            }
+          }
+          prev_stage = stage;
+        }
+        if (u >= 1) issue_pv(u - 1, prev_stage);
+      }
+      __syncwarp();
+    } else if (warp < FF_ISSUE_WARP) {
+      // ---------------------------------------------------------------------------------- drain warps
+      const int quad = warp & 3;
+      const uint32_t out_tile = smem_u32(sOut) + quad * 4096;
       int u = 0;
-      int prev_stage = 0;
-      for (int it = 0, item = blockIdx.x; item < num_items; ++it, item += gridDim.x) {
-        const int stage = it & 1;
-        const uint32_t aQ = smem_u32(smem + stage * FF_STAGE_BYTES), aK = aQ + FF_Q_BYTES;
-        const uint64_t dk = make_smem_desc_sw128(aK, 0, 1024);
-        const bool has_next = item + static_cast<int>(gridDim.x) < num_items;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        const int h = item % H, bi = item / H;
         for (int t = 0; t < nqt; ++t, ++u) {
           const int b = u & 1;
-          // buffer b is free for S(u) once O(u-2) has been drained out of its tail (P V(u-2) then has completed too)
-          if (u >= 2) mbar_wait(&bar_ofree[b], par(u - 2));
-          if (t == 0) mbar_wait(&bar_ld[stage], (it >> 1) & 1);
+          const uint32_t o_addr = tmem_base + b * 256 + FF_O_COL + (static_cast<uint32_t>(quad * 32) << 16);
+          const float* stat = sStat + b * 5 * 128;
+          const int r = quad * 32 + lane;
+          const int row = t * 128 + r;                          // query row within the item
+          const bool warp_active = t * 128 + quad * 32 < Nq;
+          mbar_wait(&bar_p[b], par(u));    // the engine's row statistics are visible
+          mbar_wait(&bar_o[b], par(u));    // P V has completed
           tc_fence_after();
-          const uint64_t dq = make_smem_desc_sw128(aQ + t * 16384, 0, 1024);
-#pragma unroll
-          for (int k = 0; k < FF_HD / 16; ++k) umma_bf16_ss(tmem_base + b * 256, dq + 2 * k, dk + 2 * k, idesc_s, k > 0 ? 1u : 0u);
-          umma_commit(&bar_s[b]);
-          FF_STAMP(u, 0);
-          // Prefetch the next item into the other operand stage once every MMA that read it has completed. Two tiles
-          // per item: those are units u-3 and u-2, and the drain of unit u-2 was awaited above. One tile per item: the
-          // reader is unit u-1, whose P V is only issued below -- prefetch after it has completed.
-          if (nqt == 2 && t == 1 && has_next) issue_loads(item + gridDim.x, stage ^ 1);
-          if (u >= 1) issue_pv(u - 1, t == 0 ? prev_stage : stage);
-          if (nqt == 1 && has_next) {
-            if (u >= 1) mbar_wait(&bar_o[b ^ 1], par(u - 1));
-            issue_loads(item + gridDim.x, stage ^ 1);
+          if (quad == 0 && lane == 0) FF_STAMP(u, 12);
+          uint32_t o0[32], o1[32];
+          float mx = 0.f, l = 1.f;
+          if (warp_active) {
+            tmem_ld_32x32b_x32(o_addr, o0);
+            tmem_ld_32x32b_x32(o_addr + 32, o1);
+            l = stat[2 * 128 + r] + stat[3 * 128 + r];
+            mx = stat[4 * 128 + r];
+            tmem_ld_wait();
           }
-        }
-        prev_stage = stage;
-      }
-      if (u >= 1) issue_pv(u - 1, prev_stage);
-    }
-    __syncwarp();
-  } else if (warp < FF_ISSUE_WARP) {
-    // ---------------------------------------------------------------------------------- drain warps
-    const int quad = warp & 3;
-    const uint32_t out_tile = smem_u32(sOut) + quad * 4096;
-    int u = 0;
-    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-      const int h = item % H, bi = item / H;
-      for (int t = 0; t < nqt; ++t, ++u) {
-        const int b = u & 1;
-        const uint32_t o_addr = tmem_base + b * 256 + FF_O_COL + (static_cast<uint32_t>(quad * 32) << 16);
-        const float* stat = sStat + b * 5 * 128;
-        const int r = quad * 32 + lane;
-        const int row = t * 128 + r;                          // query row within the item
-        const bool warp_active = t * 128 + quad * 32 < Nq;
-        mbar_wait(&bar_p[b], par(u));    // the engine's row statistics are visible
-        mbar_wait(&bar_o[b], par(u));    // P V has completed
-        tc_fence_after();
-        if (quad == 0 && lane == 0) FF_STAMP(u, 12);
-        uint32_t o0[32], o1[32];
-        float mx = 0.f, l = 1.f;
-        if (warp_active) {
-          tmem_ld_32x32b_x32(o_addr, o0);
-          tmem_ld_32x32b_x32(o_addr + 32, o1);
-          l = stat[2 * 128 + r] + stat[3 * 128 + r];
-          mx = stat[4 * 128 + r];
-          tmem_ld_wait();
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bar_ofree[b]);  // O(u) has left TMEM and the unit's statistics have been read
-        if (quad == 0 && lane == 0) FF_STAMP(u, 13);
-        if (warp_active) {
-          const float inv_l = ff_rcp(l);
-          if (lane == 0) tma_store_wait_read<0>();  // the previous unit's store has finished reading the staging tile
+          tc_fence_before();
           __syncwarp();
-          const uint32_t base = out_tile + lane * 128;
+          if (lane == 0) mbar_arrive(&bar_ofree[b]);  // O(u) has left TMEM and the unit's statistics have been read
+          if (quad == 0 && lane == 0) FF_STAMP(u, 13);
+          if (warp_active) {
+            const float inv_l = ff_rcp(l);
+            if (lane == 0) tma_store_wait_read<0>();  // the previous unit's store has finished reading the staging tile
+            __syncwarp();
+            const uint32_t base = out_tile + lane * 128;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {   // 16-byte chunks 0-3 of the row (columns 0-31), XOR-swizzled by row
-            uint32_t w[4];
+            for (int i = 0; i < 4; ++i) {   // 16-byte chunks 0-3 of the row (columns 0-31), XOR-swizzled by row
+              uint32_t w[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e)
-              w[e] = pack_bf16x2(__uint_as_float(o0[8 * i + 2 * e]) * inv_l, __uint_as_float(o0[8 * i + 2 * e + 1]) * inv_l);
-            ff_st_shared_v4(base + ((i ^ (lane & 7)) << 4), w[0], w[1], w[2], w[3]);
+              for (int e = 0; e < 4; ++e)
+                w[e] = pack_bf16x2(__uint_as_float(o0[8 * i + 2 * e]) * inv_l, __uint_as_float(o0[8 * i + 2 * e + 1]) * inv_l);
+              ff_st_shared_v4(base + ((i ^ (lane & 7)) << 4), w[0], w[1], w[2], w[3]);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {   // chunks 4-7 (columns 32-63)
+              uint32_t w[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                w[e] = pack_bf16x2(__uint_as_float(o1[8 * i + 2 * e]) * inv_l, __uint_as_float(o1[8 * i + 2 * e + 1]) * inv_l);
+              ff_st_shared_v4(base + (((4 + i) ^ (lane & 7)) << 4), w[0], w[1], w[2], w[3]);
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_3d_addr(&tm_o, out_tile, h * FF_HD, t * 128 + quad * 32, bi);
+              tma_store_commit();
+            }
+            if (lse != nullptr && row < Nq) lse[static_cast<long long>(item) * Nq + row] = (mx + ff_lg2(l)) * FF_LN2;
           }
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {   // chunks 4-7 (columns 32-63)
-            uint32_t w[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-              w[e] = pack_bf16x2(__uint_as_float(o1[8 * i + 2 * e]) * inv_l, __uint_as_float(o1[8 * i + 2 * e + 1]) * inv_l);
-            ff_st_shared_v4(base + (((4 + i) ^ (lane & 7)) << 4), w[0], w[1], w[2], w[3]);
-          }
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_3d_addr(&tm_o, out_tile, h * FF_HD, t * 128 + quad * 32, bi);
-            tma_store_commit();
-          }
-          if (lse != nullptr && row < Nq) lse[static_cast<long long>(item) * Nq + row] = (mx + ff_lg2(l)) * FF_LN2;
+          if (quad == 0 && lane == 0) FF_STAMP(u, 14);
         }
-        if (quad == 0 && lane == 0) FF_STAMP(u, 14);
       }
+      if (lane == 0) tma_store_wait_read<0>();  // the staging tile must outlive the last TMA store
     }
-    if (lane == 0) tma_store_wait_read<0>();  // the staging tile must outlive the last TMA store
-  }
   }  // roles other than the engine warps
   tc_fence_before();
   __syncthreads();
