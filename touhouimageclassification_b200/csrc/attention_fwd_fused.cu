@@ -5,8 +5,10 @@
 // One CTA per SM walks work units (image, head, 128-query tile). All keys of an item fit in ONE block, so there is no
 // online rescaling: S = Q K^T (SS MMA, M = 128 queries, N = keys rounded up to 16), row max, P = exp2(S c - max),
 // O = P V (TS MMA, P read from TMEM as packed bf16), O / rowsum -> bf16.
-// The kernel is bound by the exp2 throughput of the SFUs (16 per clock per SM); everything else is arranged so that the
-// SFUs never wait:
+// The floor is the exp2 throughput of the SFUs (16 per clock per SM: 3328 clk per (image, head) at N = 197); the roles are
+// arranged so that the SFUs wait as little as possible (measured: the exp2 pass itself runs at ~0.8 of the SFU rate, the
+// kernel as a whole at 0.55 of the floor -- the rest is the load / max / commit phases of a unit, which are issue- and
+// latency-bound):
 //   warps 0-7   softmax engine. ALL eight work on the same unit: warp w owns TMEM lane quadrant w & 3 (one query row
 //               per thread) and column half w >> 2 of the score tile, so every SM sub-partition has two warps feeding
 //               its SFU. A thread loads its <= 112 scores into registers ONCE (row max and exp2 both run from
