@@ -36,3 +36,22 @@ def test_traffic_is_only_quoted_from_a_capture_of_the_current_gemm_sources(tmp_p
     value, src = bench.committed_gemm_traffic("vitl224")
     assert value == 5.5e8 and "v2_summary" in src
     assert bench.committed_gemm_traffic("vitl384") == (None, None)   # no capture of that workload in this tree
+
+
+def test_launch_summary_reproduces_the_committed_figures(tmp_path):
+    """scripts/ncu_launch_summary.py on the committed ncu launch list of the final tree: the per-kernel shares and the DRAM
+    bytes per GEMM launch that DESIGN.md and bench.py quote come out of the raw CSV, not out of a hand-edited file."""
+    import subprocess
+    csv = os.path.join(ROOT, "profiles", "r02_launches_vitl224_v3.csv")
+    out = tmp_path / "s.json"
+    subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "ncu_launch_summary.py"), csv, "--json", str(out)],
+                   check=True, capture_output=True)
+    got = json.loads(out.read_text())
+    with open(os.path.join(ROOT, "profiles", "r02_launches_vitl224_v3_summary.json")) as f:
+        committed = json.load(f)
+    assert got["launches"] == committed["launches"] == 1000
+    assert abs(got["gemm"]["dram_bytes_per_launch"] - committed["gemm"]["dram_bytes_per_launch"]) < 1.0
+    assert 0.70 < got["gemm"]["share"] < 0.80                      # GEMMs: three quarters of the device time of a step
+    names = list(got["kernels"])
+    assert any(n.startswith("attn_bwd_fused_kernel") for n in names) and any(n.startswith("ln_bwd_kernel") for n in names)
+    assert not any("elementwise" in n and got["kernels"][n]["share"] > 0.01 for n in names)   # no library kernel above 1 %
